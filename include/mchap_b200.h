@@ -1,0 +1,165 @@
+/*
+ * mchap_b200.h — C ABI of the B200-native MCHap inference hot path.
+ *
+ * One shared library (libmchap_b200.so), plain pointers and sizes, no torch / numpy types.
+ * Every entry point returns an int status (MCHB_OK == 0); nothing throws across the ABI.
+ * The reference (PlantandFoodResearch/MCHap v0.11.1) has no FFI layer: its boundary is the
+ * Python call surface, so each entry point cites the reference function(s) it replaces
+ * (paths relative to the reference repository).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Memory spaces: `mem` tells where the BULK arrays of a call live (reads, counts, haplotypes,
+ * traces ...).  MCHB_MEM_HOST: the library stages them through the handle's stream
+ * (H2D before, D2H after).  MCHB_MEM_DEVICE: they are device pointers on the handle's device
+ * and no bulk copy is made.  Item descriptors, parameter structs and per-item result records
+ * are always HOST memory.
+ *
+ * A handle owns one device, one stream and its scratch; calls on one handle are serialised,
+ * different handles (e.g. one per host thread) run concurrently.
+ */
+#ifndef MCHAP_B200_H
+#define MCHAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCHB_VERSION 1
+
+/* ---- status codes (library level) ---- */
+#define MCHB_OK 0
+#define MCHB_ERR_CUDA 100         /* a CUDA runtime call failed: see mchb_last_error */
+#define MCHB_ERR_ARGUMENT 101     /* inconsistent sizes / null pointers */
+#define MCHB_ERR_NO_DEVICE 102    /* no usable sm_100 device: the library never falls back to the CPU */
+
+/* ---- per-item status codes (mchb_item_result.status) ---- */
+#define MCHB_ITEM_OK 0
+#define MCHB_ITEM_NAN_LLK 1        /* reference: ValueError("Encountered log likelihood of nan"), assemble/mcmc.py:330-331 */
+#define MCHB_ITEM_BREAKS 2         /* reference: ValueError("breaks must be smaller then n"), assemble/structural.py:49-50 */
+#define MCHB_ITEM_CHOICE_RANGE 4   /* random_choice returned len(p) where the reference indexes out of range (jitutils.py:92) */
+#define MCHB_ITEM_INITIAL_SHAPE 5  /* reference: AssertionError, assemble/mcmc.py:207 */
+#define MCHB_ITEM_RNG_EXHAUSTED 6  /* pre-drawn word stream too short (the host shim retries with a longer one) */
+#define MCHB_ITEM_UNSUPPORTED 8    /* shape outside the compiled limits (see mchb_limits); never silently approximated */
+
+#define MCHB_MEM_HOST 0
+#define MCHB_MEM_DEVICE 1
+
+typedef struct mchb_handle mchb_handle;
+
+typedef struct {
+    int32_t max_ploidy;          /* 16 */
+    int32_t max_key_bits;        /* 64: n_het_positions * bits_per_allele must fit */
+    int32_t max_unique_reads;    /* 256 per item for the warp-resident MCMC kernels */
+    int32_t max_temperatures;    /* 8 */
+    int32_t max_haplotypes;      /* 256 known haplotypes per locus for call / call-exact */
+} mchb_limits;
+
+typedef struct {
+    int32_t status;       /* MCHB_ITEM_* */
+    int32_t n_het;        /* assemble: positions left variable after homozygous fixing */
+    int64_t rng_words;    /* 32-bit MT19937 words consumed by the item (== numba's cursor advance) */
+    int64_t llk_evals;    /* log_likelihood evaluations performed (algorithmic work counter) */
+} mchb_item_result;
+
+/* ---- lifecycle ---- */
+int mchb_create(int device, mchb_handle **out);
+void mchb_destroy(mchb_handle *h);
+const char *mchb_last_error(const mchb_handle *h);
+void mchb_get_limits(mchb_limits *out);
+/* device time (ms, CUDA events on the handle's stream) of the kernels of the last call and
+ * how many kernels this library launched in it */
+float mchb_last_kernel_ms(const mchb_handle *h);
+int32_t mchb_last_kernel_launches(const mchb_handle *h);
+/* the cudaStream_t the handle launches on (for external event timing) */
+void *mchb_stream(const mchb_handle *h);
+int mchb_sm_count(const mchb_handle *h);
+
+/* ---- RNG: numba's np.random MT19937 stream -------------------------------------------
+ * Replaces: numba's thread-local generator as the reference drives it (jitutils.py:180-183
+ * seed_numba; numba/cpython/randomimpl.py get_next_int32).  Fills `out` (n words, space `mem`)
+ * with the tempered 32-bit output stream of init_genrand(seed). */
+int mchb_mt19937_words(mchb_handle *h, int mem, uint32_t seed, uint32_t *out, int64_t n);
+
+/* ---- multiset rank / unrank (bit-exact integers) -------------------------------------
+ * Replaces: jitutils.py:253-276 genotype_alleles_as_index, 279-318 index_as_genotype_alleles
+ * (VCF order).  alleles int64[n, ploidy] (sorted ascending per row), index int64[n].
+ * unrank writes -1 alleles for index < 0 (the reference returns None). */
+int mchb_genotype_rank(mchb_handle *h, int mem, const int64_t *alleles, int64_t n, int32_t ploidy,
+                       int64_t *out_index);
+int mchb_genotype_unrank(mchb_handle *h, int mem, const int64_t *index, int64_t n, int32_t ploidy,
+                         int64_t *out_alleles);
+
+/* ---- read log-likelihood, batched -----------------------------------------------------
+ * Replaces: assemble/likelihood.py:18-70 log_likelihood for n (reads, genotype) pairs.
+ * Item i: reads f64[U,N,A] at reads + reads_off[i]; counts i64[U] at counts + counts_off[i]
+ * (counts == NULL: unweighted); genotype int8[P,N] at genotypes + geno_off[i]. */
+typedef struct {
+    int64_t reads_off, counts_off, geno_off;
+    int32_t n_reads, n_pos, max_allele, ploidy;
+} mchb_llk_item;
+
+int mchb_log_likelihood_batch(mchb_handle *h, int mem, const mchb_llk_item *items, int64_t n_items,
+                              const double *reads, int64_t reads_len, const int64_t *counts,
+                              int64_t counts_len, const int8_t *genotypes, int64_t genotypes_len,
+                              double *out_llk);
+
+/* ---- de novo assembly MCMC, batched -----------------------------------------------------
+ * Replaces: assemble/mcmc.py:103-265 DenovoMCMC.fit/_mcmc (homozygous fixing 495-541 via
+ * snpcalling.py:14-70, initial state 455-491 + jitutils.py:465-498), 269-426 _denovo_assembler,
+ * mutation.py:15-246, structural.py:23-673, tempering.py:11-151, prior.py:15-112 — one call
+ * per batch of (locus, sample) items instead of one fit() per item.
+ *
+ * Item i: reads f64[U,N,A], counts i64[U] (or none), n_alleles int8[N], optional initial
+ * int8[chains, P, initial_nhet]; outputs genotypes int8[chains, steps, P, N] at
+ * out_genotypes + genotypes_off (fixed homozygous alleles re-inserted, haplotypes in sampler
+ * order — the reference sorts them later in GenotypeMultiTrace.__post_init__) and llks
+ * f64[chains, steps] at out_llks + llks_off.  The RNG stream of an item is the MT19937
+ * stream of `seed` from its start (the reference re-seeds at the top of every fit), consumed
+ * with numba's word->value rules in the reference's call order: chains one after another,
+ * temperatures ascending inside a step. */
+typedef struct {
+    int64_t reads_off;       /* doubles */
+    int64_t counts_off;      /* int64 elements; ignored if counts == NULL */
+    int64_t nalleles_off;    /* int8 elements */
+    int64_t initial_off;     /* int8 elements; -1: sample the initial state like the reference */
+    int64_t genotypes_off;   /* int8 elements into out_genotypes */
+    int64_t llks_off;        /* doubles into out_llks */
+    int32_t n_reads, n_pos, max_allele, ploidy;
+    int32_t temps_off, n_temps; /* temperatures[temps_off .. +n_temps): ascending, last == 1.0 */
+    int32_t initial_nhet;
+    uint32_t seed;
+    double inbreeding;       /* NaN: flat prior (reference inbreeding=None) */
+} mchb_assemble_item;
+
+typedef struct {
+    int32_t steps, chains;
+    double fix_homozygous;
+    double p_recombination, p_partial_dosage, p_dosage;
+    /* row n (0..break_rows-1) = distribution of the number of break points when n positions
+     * stay variable (assemble/mcmc.py:211-217; rows are computed on the host with scipy exactly
+     * like _point_beta_probabilities 429-452); f64[break_rows * break_stride], lengths int32 */
+    const double *break_table;
+    const int32_t *break_len;
+    int32_t break_rows, break_stride;
+    const double *temperatures; /* pool indexed by item.temps_off */
+    int32_t temperatures_len;
+    /* replay harness: when replay_words != NULL every item reads this pre-drawn (tempered)
+     * 32-bit stream from word 0 instead of MT19937(seed) (always HOST memory) */
+    const uint32_t *replay_words;
+    int64_t replay_len;
+    int64_t rng_words_hint;  /* 0: estimate; else initial per-stream length in words */
+} mchb_assemble_params;
+
+int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *params,
+                        const mchb_assemble_item *items, int64_t n_items, const double *reads,
+                        int64_t reads_len, const int64_t *counts, int64_t counts_len,
+                        const int8_t *n_alleles, int64_t n_alleles_len, const int8_t *initial,
+                        int64_t initial_len, int8_t *out_genotypes, int64_t out_genotypes_len,
+                        double *out_llks, int64_t out_llks_len, mchb_item_result *results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCHAP_B200_H */

@@ -1,0 +1,206 @@
+"""Batched host API over the C ABI: numpy in, numpy out (or raw device pointers in device mode).
+
+The single-item, reference-shaped entry points (``DenovoMCMC.fit`` ...) live in
+``mchap_b200.assemble`` / ``mchap_b200.calling`` and call into this module.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+ASSEMBLE_ITEM_DTYPE = L._np_dtype(L.AssembleItem)
+LLK_ITEM_DTYPE = L._np_dtype(L.LlkItem)
+ITEM_RESULT_DTYPE = L._np_dtype(L.ItemResult)
+
+_ITEM_ERRORS = {
+    L.ITEM_NAN_LLK: (ValueError, "Encountered log likelihood of nan"),
+    L.ITEM_BREAKS: (ValueError, "breaks must be smaller then n"),
+    L.ITEM_CHOICE_RANGE: (IndexError, "random_choice selected an option beyond the end of its probability vector"),
+    L.ITEM_INITIAL_SHAPE: (AssertionError, "initial genotype does not have shape (ploidy, n_het_base)"),
+    L.ITEM_RNG_EXHAUSTED: (RuntimeError, "pre-drawn random word stream exhausted"),
+    L.ITEM_UNSUPPORTED: (NotImplementedError, "item shape is outside the limits of the CUDA kernels (see mchb_get_limits)"),
+}
+
+
+class MchapB200Error(RuntimeError):
+    pass
+
+
+def raise_item_status(status, index=None):
+    """Re-raise a per-item device status with the reference's exception type and message."""
+    if status == L.ITEM_OK:
+        return
+    exc, msg = _ITEM_ERRORS.get(int(status), (MchapB200Error, "device status %d" % status))
+    if index is not None:
+        msg = "%s (item %d)" % (msg, index)
+    raise exc(msg)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+class Device:
+    """One handle = one GPU + one stream (see include/mchap_b200.h)."""
+
+    def __init__(self, device=0):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.mchb_create(int(device), C.byref(h))
+        if rc == L.MCHB_ERR_NO_DEVICE:
+            raise MchapB200Error(
+                "no sm_100 (B200) CUDA device %d: mchap_b200 has no CPU fallback" % device)
+        if rc != L.MCHB_OK:
+            raise MchapB200Error("mchb_create failed with status %d" % rc)
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mchb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != L.MCHB_OK:
+            msg = self._lib.mchb_last_error(self._h)
+            raise MchapB200Error("status %d: %s" % (rc, msg.decode() if msg else ""))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self._lib.mchb_last_kernel_ms(self._h))
+
+    @property
+    def last_kernel_launches(self):
+        return int(self._lib.mchb_last_kernel_launches(self._h))
+
+    @property
+    def sm_count(self):
+        return int(self._lib.mchb_sm_count(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.mchb_stream(self._h)
+
+    @staticmethod
+    def limits():
+        lim = L.Limits()
+        L.load().mchb_get_limits(C.byref(lim))
+        return {f[0]: getattr(lim, f[0]) for f in lim._fields_}
+
+    # ------------------------------------------------------------------ RNG / ranking
+    def mt19937_words(self, seed, n):
+        """numba's MT19937 output stream after np.random.seed(seed) (jitutils.py:180-183)."""
+        out = np.empty(int(n), dtype=np.uint32)
+        self._check(self._lib.mchb_mt19937_words(self._h, L.MEM_HOST, int(seed), _ptr(out), int(n)))
+        return out
+
+    def genotype_alleles_as_index(self, alleles):
+        """jitutils.py:253-276 for an int array [n, ploidy] of sorted alleles."""
+        a = np.ascontiguousarray(alleles, dtype=np.int64)
+        assert a.ndim == 2
+        out = np.empty(a.shape[0], dtype=np.int64)
+        self._check(self._lib.mchb_genotype_rank(self._h, L.MEM_HOST, _ptr(a), a.shape[0], a.shape[1], _ptr(out)))
+        return out
+
+    def index_as_genotype_alleles(self, index, ploidy):
+        """jitutils.py:279-318 for an int array [n] (negative index -> -1 alleles)."""
+        i = np.ascontiguousarray(index, dtype=np.int64)
+        out = np.empty((i.shape[0], int(ploidy)), dtype=np.int64)
+        self._check(self._lib.mchb_genotype_unrank(self._h, L.MEM_HOST, _ptr(i), i.shape[0], int(ploidy), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ K1
+    def log_likelihood_batch(self, reads_list, genotypes_list, counts_list=None):
+        """assemble/likelihood.py:18-70 for many (reads, genotype[, counts]) triples."""
+        n = len(reads_list)
+        items = np.zeros(n, dtype=LLK_ITEM_DTYPE)
+        ro = go = co = 0
+        rs, gs, cs = [], [], []
+        use_counts = counts_list is not None and any(c is not None for c in counts_list)
+        for i in range(n):
+            r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
+            g = np.ascontiguousarray(genotypes_list[i], dtype=np.int8)
+            assert r.ndim == 3 and g.ndim == 2 and g.shape[1] == r.shape[1]
+            items[i] = (ro, co, go, r.shape[0], r.shape[1], r.shape[2], g.shape[0])
+            rs.append(r.ravel())
+            gs.append(g.ravel())
+            ro += r.size
+            go += g.size
+            if use_counts:
+                c = counts_list[i]
+                c = np.ones(r.shape[0], dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64)
+                cs.append(c)
+                co += c.size
+        reads = np.concatenate(rs) if rs else np.zeros(0)
+        genos = np.concatenate(gs) if gs else np.zeros(0, dtype=np.int8)
+        counts = np.concatenate(cs) if use_counts else None
+        out = np.empty(n, dtype=np.float64)
+        self._check(self._lib.mchb_log_likelihood_batch(
+            self._h, L.MEM_HOST, _ptr(items), n, _ptr(reads), reads.size, _ptr(counts),
+            0 if counts is None else counts.size, _ptr(genos), genos.size, _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ K2
+    def assemble_call(self, items, params, reads, counts, n_alleles, initial, out_genotypes, out_llks,
+                      lens, mem=L.MEM_HOST, keepalive=()):
+        """Thin wrapper of mchb_assemble_batch. ``items`` is a structured array of
+        ASSEMBLE_ITEM_DTYPE; bulk arrays are numpy arrays (host) or integer device pointers;
+        ``lens`` = (reads_len, counts_len, n_alleles_len, initial_len, genotypes_len, llks_len)."""
+        n = len(items)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        rc = self._lib.mchb_assemble_batch(
+            self._h, mem, C.byref(params), _ptr(items), n, _ptr(reads), int(lens[0]), _ptr(counts), int(lens[1]),
+            _ptr(n_alleles), int(lens[2]), _ptr(initial), int(lens[3]), _ptr(out_genotypes), int(lens[4]),
+            _ptr(out_llks), int(lens[5]), _ptr(results))
+        self._check(rc)
+        return results
+
+
+def make_assemble_params(steps, chains, fix_homozygous, p_recombination, p_partial_dosage, p_dosage,
+                         break_table, break_len, temperatures, replay_words=None, rng_words_hint=0):
+    """Build the parameter struct; returns (params, keepalive tuple of the arrays it points to)."""
+    bt = np.ascontiguousarray(break_table, dtype=np.float64)
+    bl = np.ascontiguousarray(break_len, dtype=np.int32)
+    tp = np.ascontiguousarray(temperatures, dtype=np.float64)
+    rw = None if replay_words is None else np.ascontiguousarray(replay_words, dtype=np.uint32)
+    p = L.AssembleParams()
+    p.steps = int(steps)
+    p.chains = int(chains)
+    p.fix_homozygous = float(fix_homozygous)
+    p.p_recombination = float(p_recombination)
+    p.p_partial_dosage = float(p_partial_dosage)
+    p.p_dosage = float(p_dosage)
+    p.break_table = bt.ctypes.data
+    p.break_len = bl.ctypes.data
+    p.break_rows = bt.shape[0]
+    p.break_stride = bt.shape[1]
+    p.temperatures = tp.ctypes.data
+    p.temperatures_len = tp.size
+    p.replay_words = None if rw is None else rw.ctypes.data
+    p.replay_len = 0 if rw is None else rw.size
+    p.rng_words_hint = int(rng_words_hint)
+    return p, (bt, bl, tp, rw)
+
+
+_default_devices = {}
+
+
+def default_device(device=0):
+    """Process-wide handle per GPU ordinal (created on first use)."""
+    d = _default_devices.get(device)
+    if d is None:
+        d = Device(device)
+        _default_devices[device] = d
+    return d

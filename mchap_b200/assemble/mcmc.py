@@ -1,0 +1,164 @@
+"""``DenovoMCMC`` with the reference's constructor and ``fit`` signature
+(reference: mchap/assemble/mcmc.py:24-161), executed by the CUDA kernel ``assemble_kernel``.
+
+``fit`` handles one (locus, sample) item like the reference; ``fit_batch`` sends many items in
+one device call (the reason this package exists).  There is no CPU path.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+from .. import _lib as L
+from ..api import ASSEMBLE_ITEM_DTYPE, default_device, make_assemble_params, raise_item_status
+from .classes import GenotypeMultiTrace
+
+__all__ = ["DenovoMCMC", "point_beta_probabilities", "break_table"]
+
+
+def point_beta_probabilities(n_base, a=1.0, b=3.0):
+    """P(number of break points = k), k = 0..n_base-1: CDF differences of Beta(a, b) on the grid
+    k / n_base.  Host-side scipy call, as in the reference (mcmc.py:429-452)."""
+    from scipy import stats
+
+    grid = np.arange(1, n_base + 1) / n_base
+    cdf = stats.beta(a, b).cdf(grid)
+    cdf[1:] = cdf[1:] - cdf[:-1]
+    return cdf
+
+
+def break_table(n_pos, alpha=1.0, beta=3.0, n_intervals=None):
+    """Row n = break-point distribution used when n positions stay variable (mcmc.py:211-217)."""
+    stride = max(int(n_pos), int(n_intervals or 0), 1)
+    table = np.zeros((n_pos + 1, stride), dtype=np.float64)
+    lens = np.zeros(n_pos + 1, dtype=np.int32)
+    for n in range(1, n_pos + 1):
+        if n_intervals is None:
+            row = point_beta_probabilities(n, alpha, beta)
+        else:
+            row = np.zeros(n_intervals, dtype=np.float64)
+            row[-1] = 1
+        table[n, : len(row)] = row
+        lens[n] = len(row)
+    return table, lens
+
+
+@dataclass
+class DenovoMCMC(object):
+    ploidy: int
+    n_alleles: list
+    inbreeding: float = None
+    steps: int = 1000
+    chains: int = 2
+    alpha: float = 1.0
+    beta: float = 3.0
+    n_intervals: int = None
+    fix_homozygous: float = 0.999
+    recombination_step_probability: float = 0.5
+    partial_dosage_step_probability: float = 0.5
+    dosage_step_probability: float = 1.0
+    temperatures: tuple = (1.0,)
+    random_seed: int = None
+    llk_cache_threshold: int = 100  # accepted for signature parity; the GPU path caches per-haplotype products instead
+    device: object = None
+
+    @classmethod
+    def parameterize(cls, *args, **kwargs):
+        return cls(*args, **kwargs)
+
+    def _temperatures(self):
+        temps = np.sort(np.asarray(self.temperatures, dtype=np.float64))
+        assert temps[0] >= 0.0
+        assert temps[-1] == 1.0
+        return temps
+
+    def _seed(self):
+        if self.random_seed is not None:
+            return int(self.random_seed) & 0xFFFFFFFF
+        return int(np.random.randint(0, 2 ** 32, dtype=np.uint64))
+
+    def fit(self, reads, read_counts=None, initial=None):
+        """Same contract as the reference's fit: returns a GenotypeMultiTrace with genotypes
+        int8[chains, steps, ploidy, n_positions] (haplotypes sorted per step) and llks."""
+        res = self.fit_batch([reads], [read_counts], None if initial is None else [initial])
+        return res[0]
+
+    def fit_batch(self, reads_list, counts_list=None, initial_list=None, n_alleles_list=None,
+                  seeds=None, return_results=False, raw=False, replay_words=None):
+        """Run ``fit`` for many items in one device call.
+
+        n_alleles_list: per item allele counts (default: self.n_alleles for every item);
+        seeds: per item seeds (default: self.random_seed for every item, like the CLIs);
+        raw=True returns unsorted (genotypes, llks) arrays instead of GenotypeMultiTrace."""
+        dev = self.device or default_device()
+        n = len(reads_list)
+        temps = self._temperatures()
+        items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
+        rs, cs, ns, ins = [], [], [], []
+        ro = co = no = io = go = lo = 0
+        use_counts = counts_list is not None and any(c is not None for c in counts_list)
+        use_initial = initial_list is not None and any(i is not None for i in initial_list)
+        seed0 = self._seed()
+        shapes = []
+        nmax = 1
+        for i in range(n):
+            r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
+            assert r.ndim == 3
+            U, N, A = r.shape
+            na = np.ascontiguousarray(self.n_alleles if n_alleles_list is None else n_alleles_list[i], dtype=np.int8)
+            assert len(na) == N
+            nmax = max(nmax, N)
+            it = items[i]
+            it["reads_off"], it["counts_off"], it["nalleles_off"] = ro, co, no
+            it["genotypes_off"], it["llks_off"] = go, lo
+            it["n_reads"], it["n_pos"], it["max_allele"], it["ploidy"] = U, N, max(A, 1), self.ploidy
+            it["temps_off"], it["n_temps"] = 0, len(temps)
+            it["seed"] = seed0 if seeds is None else int(seeds[i]) & 0xFFFFFFFF
+            it["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
+            it["initial_off"] = -1
+            if use_initial and initial_list[i] is not None:
+                ini = np.ascontiguousarray(initial_list[i], dtype=np.int8)
+                assert ini.ndim == 3 and ini.shape[0] == self.chains and ini.shape[1] == self.ploidy
+                it["initial_off"] = io
+                it["initial_nhet"] = ini.shape[2]
+                ins.append(ini.ravel())
+                io += ini.size
+            rs.append(r.ravel())
+            ns.append(na)
+            ro += r.size
+            no += N
+            if use_counts:
+                c = counts_list[i]
+                c = np.ones(U, dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64)
+                assert len(c) == U or U == 0
+                cs.append(c[:U])
+                co += U
+            shapes.append((N, go, lo))
+            go += self.chains * self.steps * self.ploidy * N
+            lo += self.chains * self.steps
+        reads = np.concatenate(rs) if rs else np.zeros(0)
+        nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
+        counts = np.concatenate(cs) if use_counts and cs else None
+        initial = np.concatenate(ins) if ins else None
+        out_g = np.zeros(max(go, 1), dtype=np.int8)
+        out_l = np.full(max(lo, 1), np.nan, dtype=np.float64)
+        table, lens = break_table(nmax, self.alpha, self.beta, self.n_intervals)
+        params, keep = make_assemble_params(
+            self.steps, self.chains, self.fix_homozygous, self.recombination_step_probability,
+            self.partial_dosage_step_probability, self.dosage_step_probability, table, lens, temps,
+            replay_words=replay_words)
+        results = dev.assemble_call(
+            items, params, reads, counts, nall, initial, out_g, out_l,
+            (reads.size, 0 if counts is None else counts.size, nall.size, 0 if initial is None else initial.size,
+             go, lo))
+        out = []
+        for i, (N, g0, l0) in enumerate(shapes):
+            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+            g = out_g[g0: g0 + self.chains * self.steps * self.ploidy * N].reshape(
+                self.chains, self.steps, self.ploidy, N)
+            l = out_l[l0: l0 + self.chains * self.steps].reshape(self.chains, self.steps)
+            if N == 0:
+                l[:] = np.nan  # no variable position: nothing was sampled (mcmc.py:188-199)
+            out.append((g, l) if raw else GenotypeMultiTrace(g, l))
+        if return_results:
+            return out, results
+        return out

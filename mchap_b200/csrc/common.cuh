@@ -1,0 +1,190 @@
+// common.cuh — device-side building blocks shared by the sm_100a kernels.
+//
+// Conventions
+//  * one warp owns one (locus, sample) item; "uniform" values are held identically by all
+//    32 lanes (every lane executes the scalar control flow, so no broadcasts are needed);
+//  * per-read data is distributed over lanes: read r lives in lane r%32, chunk r/32;
+//  * compiled with -fmad=false: the reference (numba, no fast-math) never contracts a*b+c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/mchap_b200.h"
+
+#define MCHB_MAX_PLOIDY 16
+#define MCHB_MAX_TEMPS 8
+#define MCHB_FULL 0xffffffffu
+
+namespace mchb {
+
+// Host-initialised tables (glibc values, so integer-argument logs / lgammas are bit-identical
+// to what numba calls on the CPU).  k < MCHB_TABLE_N.
+//   LOG_INT[k] = log(k) (LOG_INT[0] = -inf), LOG_INV_INT[k] = log(1.0 / k),
+//   LGAMMA_INT[k] = lgamma(k), LOGF_INT[k] = logf((float)k)
+#define MCHB_TABLE_N 272
+__constant__ double LOG_INT[MCHB_TABLE_N];
+__constant__ double LOG_INV_INT[MCHB_TABLE_N];
+__constant__ double LGAMMA_INT[MCHB_TABLE_N];
+__constant__ float LOGF_INT[MCHB_TABLE_N];
+
+// ---------------------------------------------------------------------------------------
+// Word source: numba's MT19937 output stream, pre-generated in global memory (tempered
+// words).  Each lane keeps one word of the current 32-word block and of the next block in
+// registers; next_u32() is a warp shuffle.  Cursor is warp-uniform.
+// Reference semantics: numba/cpython/randomimpl.py get_next_int32 109-132.
+// ---------------------------------------------------------------------------------------
+struct WordStream {
+    const uint32_t *base;
+    int64_t len;      // words available
+    int64_t cur;      // words consumed so far (uniform)
+    uint32_t w_cur;   // lane's word of block cur/32
+    uint32_t w_next;  // lane's word of block cur/32 + 1
+    int exhausted;
+
+    __device__ __forceinline__ uint32_t load_block(int64_t blk, int lane) const {
+        int64_t i = blk * 32 + lane;
+        return (i < len) ? __ldg(base + i) : 0u;
+    }
+    __device__ __forceinline__ void init(const uint32_t *b, int64_t n, int lane) {
+        base = b;
+        len = n;
+        cur = 0;
+        exhausted = 0;
+        w_cur = load_block(0, lane);
+        w_next = load_block(1, lane);
+    }
+    __device__ __forceinline__ uint32_t next_u32(int lane) {
+        int k = (int)(cur & 31);
+        uint32_t w = __shfl_sync(MCHB_FULL, w_cur, k);
+        if (cur >= len) exhausted = 1;
+        cur++;
+        if (k == 31) {
+            w_cur = w_next;
+            w_next = load_block((cur >> 5) + 1, lane);
+        }
+        return w;
+    }
+    // randomimpl.py:134-147 get_next_double
+    __device__ __forceinline__ double next_double(int lane) {
+        uint32_t a = next_u32(lane) >> 5;
+        uint32_t b = next_u32(lane) >> 6;
+        return ((double)b + (double)a * 67108864.0) / 9007199254740992.0;
+    }
+    // randomimpl.py:454-520 _randrange_impl (state "np", n <= 2^31 here); n == 1 draws nothing
+    __device__ __forceinline__ int randint(int n, int lane) {
+        if (n == 1) return 0;
+        int nbits = 32 - __clz(n - 1);
+        uint32_t mask = 0xffffffffu >> (32 - nbits);
+        for (;;) {
+            uint32_t r = next_u32(lane) & mask;
+            if ((int)r < n) return (int)r;
+            if (exhausted) return 0;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// log-space helpers (jitutils.py:6-74)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double add_log_prob(double x, double y) {
+    if (x == -INFINITY && y == -INFINITY) return -INFINITY;
+    if (x > y) return x + log1p(exp(y - x));
+    return y + log1p(exp(x - y));
+}
+
+// np.minimum(0.0, x): NaN propagates
+__device__ __forceinline__ double np_minimum0(double x) {
+    if (isnan(x)) return x;
+    return x < 0.0 ? x : 0.0;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(MCHB_FULL, v, m);
+    return v;  // bit-identical in every lane (fp add commutes)
+}
+
+// searchsorted(cumsum, u, side="right") on a uniform smem array (numba arraymath.py:3841-3860)
+__device__ __forceinline__ int searchsorted_right(const double *cs, int n, double u) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (cs[mid] <= u) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact integer binomials (jitutils.py:186-250)
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t gcd_i64(int64_t x, int64_t y) {
+    while (y != 0) {
+        int64_t t = x % y;
+        x = y;
+        y = t;
+    }
+    return x;
+}
+__host__ __device__ inline int64_t comb_exact(int64_t n, int64_t k) {
+    if (k > n) return 0;
+    int64_t r = 1;
+    for (int64_t d = 1; d <= k; d++) {
+        int64_t g = gcd_i64(r, d);
+        r /= g;
+        r *= n;
+        r /= d / g;
+        n -= 1;
+    }
+    return r;
+}
+__host__ __device__ inline int64_t comb_with_replacement(int64_t n, int64_t k) {
+    if (n == 0 && k == 0) return 0;  // jitutils.py:232-233
+    return comb_exact(n + k - 1, k);
+}
+
+// calling/prior.py:116-179 log_genotype_prior with frequencies == None or given.
+// g: sorted or unsorted allele indices (uniform array in local/shared memory), P <= 16.
+__device__ inline double calling_log_genotype_prior(const int *g, int P, int H, double inbreeding,
+                                                    const double *freqs) {
+    int dosage[MCHB_MAX_PLOIDY];
+    for (int i = 0; i < P; i++) dosage[i] = 0;
+    for (int i = 0; i < P; i++) {  // calling/utils.py:7-35 allelic_dosage
+        int j = 0;
+        while (g[j] != g[i]) j++;
+        dosage[j] += 1;
+    }
+    if (inbreeding == 0.0) {
+        double ln_num = LGAMMA_INT[P + 1];
+        double ln_denom = 0.0;
+        for (int i = 0; i < P; i++) ln_denom += LGAMMA_INT[dosage[i] + 1];
+        double ln_perms = ln_num - ln_denom;
+        if (!freqs) return ln_perms - (double)P * log((double)H);
+        double prod = 1.0;
+        for (int i = 0; i < P; i++) prod *= freqs[g[i]];
+        return ln_perms + log(prod);
+    }
+    double scale = (1.0 - inbreeding) / inbreeding;
+    double alpha_const = 0.0, sum_alphas = 0.0;
+    if (!freqs) {
+        alpha_const = (1.0 / (double)H) * scale;
+        sum_alphas = alpha_const * (double)H;
+    } else {
+        for (int a = 0; a < H; a++) sum_alphas += freqs[a] * scale;
+    }
+    double left = (LGAMMA_INT[P + 1] + lgamma(sum_alphas)) - lgamma((double)P + sum_alphas);
+    double prod = 0.0;
+    for (int i = 0; i < P; i++) {
+        int dose = dosage[i];
+        if (dose > 0) {
+            double alpha_i = freqs ? freqs[g[i]] * scale : alpha_const;
+            double num = lgamma((double)dose + alpha_i);
+            double den = LGAMMA_INT[dose + 1] + lgamma(alpha_i);
+            prod += num - den;
+        }
+    }
+    return left + prod;
+}
+
+}  // namespace mchb

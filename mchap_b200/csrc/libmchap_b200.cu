@@ -1,0 +1,576 @@
+// libmchap_b200.cu — the C ABI (include/mchap_b200.h) over the sm_100a kernels.
+// Unity build: the kernel headers are included here so that the __constant__ tables exist once.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//             -Xcompiler -fPIC -shared -cudart static
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "common.cuh"
+#include "aux_kernels.cuh"
+#include "assemble_kernel.cuh"
+
+using namespace mchb;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct mchb_handle {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    float kernel_ms = 0.f;
+    int32_t launches = 0;
+    std::vector<DevBuf> bufs;  // scratch slots, grown on demand
+};
+
+namespace {
+
+enum Slot {
+    S_ITEMS = 0, S_ORDER, S_READS, S_COUNTS, S_NALLELES, S_INITIAL, S_OUT_G, S_OUT_L, S_RESULTS,
+    S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
+    S_NSLOTS
+};
+
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+            return MCHB_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+int ensure(mchb_handle *h, int slot, size_t bytes, void **out) {
+    DevBuf &b = h->bufs[slot];
+    if (bytes > b.cap) {
+        if (b.p) CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+        size_t cap = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return MCHB_OK;
+}
+
+// bring a bulk input array to the device (or pass a device pointer through)
+template <typename T>
+int stage_in(mchb_handle *h, int mem, int slot, const T *src, int64_t n, const T **dev) {
+    if (!src || n <= 0) {
+        *dev = nullptr;
+        return MCHB_OK;
+    }
+    if (mem == MCHB_MEM_DEVICE) {
+        *dev = src;
+        return MCHB_OK;
+    }
+    void *p;
+    int rc = ensure(h, slot, sizeof(T) * (size_t)n, &p);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(p, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    *dev = static_cast<const T *>(p);
+    return MCHB_OK;
+}
+
+template <typename T>
+int stage_out(mchb_handle *h, int mem, int slot, T *dst, int64_t n, T **dev) {
+    if (mem == MCHB_MEM_DEVICE) {
+        *dev = dst;
+        return MCHB_OK;
+    }
+    void *p;
+    int rc = ensure(h, slot, sizeof(T) * (size_t)std::max<int64_t>(n, 1), &p);
+    if (rc) return rc;
+    *dev = static_cast<T *>(p);
+    return MCHB_OK;
+}
+
+bool g_tables_ready[64] = {false};
+
+int init_tables(mchb_handle *h) {
+    if (h->device < 64 && g_tables_ready[h->device]) return MCHB_OK;
+    static double log_int[MCHB_TABLE_N], log_inv[MCHB_TABLE_N], lgam[MCHB_TABLE_N];
+    static float logf_int[MCHB_TABLE_N];
+    for (int k = 0; k < MCHB_TABLE_N; k++) {
+        log_int[k] = std::log((double)k);  // log(0) = -inf
+        log_inv[k] = k > 0 ? std::log(1.0 / (double)k) : INFINITY;
+        lgam[k] = k > 0 ? std::lgamma((double)k) : INFINITY;
+        logf_int[k] = ::logf((float)k);
+    }
+    CK(cudaMemcpyToSymbol(LOG_INT, log_int, sizeof(log_int)));
+    CK(cudaMemcpyToSymbol(LOG_INV_INT, log_inv, sizeof(log_inv)));
+    CK(cudaMemcpyToSymbol(LGAMMA_INT, lgam, sizeof(lgam)));
+    CK(cudaMemcpyToSymbol(LOGF_INT, logf_int, sizeof(logf_int)));
+    if (h->device < 64) g_tables_ready[h->device] = true;
+    return MCHB_OK;
+}
+
+void begin_call(mchb_handle *h) {
+    h->err.clear();
+    h->kernel_ms = 0.f;
+    h->launches = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mchb_create(int device, mchb_handle **out) {
+    if (!out) return MCHB_ERR_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return MCHB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MCHB_ERR_NO_DEVICE;
+    if (prop.major != 10) return MCHB_ERR_NO_DEVICE;  // sm_100a code only: no fallback of any kind
+    mchb_handle *h = new mchb_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->bufs.resize(S_NSLOTS);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return MCHB_ERR_CUDA;
+    }
+    int rc = init_tables(h);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return MCHB_OK;
+}
+
+void mchb_destroy(mchb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto &b : h->bufs)
+        if (b.p) cudaFree(b.p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char *mchb_last_error(const mchb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+void mchb_get_limits(mchb_limits *out) {
+    if (!out) return;
+    out->max_ploidy = MCHB_MAX_PLOIDY;
+    out->max_key_bits = 64;
+    out->max_unique_reads = 256;
+    out->max_temperatures = MCHB_MAX_TEMPS;
+    out->max_haplotypes = 256;
+}
+
+float mchb_last_kernel_ms(const mchb_handle *h) { return h ? h->kernel_ms : 0.f; }
+int32_t mchb_last_kernel_launches(const mchb_handle *h) { return h ? h->launches : 0; }
+void *mchb_stream(const mchb_handle *h) { return h ? (void *)h->stream : nullptr; }
+int mchb_sm_count(const mchb_handle *h) { return h ? h->sm_count : 0; }
+
+// ------------------------------------------------------------------------------------- RNG
+static int fill_streams(mchb_handle *h, const std::vector<uint32_t> &seeds, int64_t len, uint32_t **words) {
+    void *dseeds, *dwords;
+    int rc = ensure(h, S_SEEDS, sizeof(uint32_t) * seeds.size(), &dseeds);
+    if (rc) return rc;
+    rc = ensure(h, S_WORDS, sizeof(uint32_t) * seeds.size() * (size_t)len, &dwords);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dseeds, seeds.data(), sizeof(uint32_t) * seeds.size(), cudaMemcpyHostToDevice, h->stream));
+    mt19937_fill_kernel<<<(unsigned)seeds.size(), 256, 0, h->stream>>>((const uint32_t *)dseeds, (uint32_t *)dwords, len);
+    CK(cudaGetLastError());
+    h->launches++;
+    *words = (uint32_t *)dwords;
+    return MCHB_OK;
+}
+
+int mchb_mt19937_words(mchb_handle *h, int mem, uint32_t seed, uint32_t *out, int64_t n) {
+    if (!h || !out || n < 0) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return MCHB_OK;
+    std::vector<uint32_t> seeds(1, seed);
+    uint32_t *words;
+    int rc = fill_streams(h, seeds, n, &words);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, words, sizeof(uint32_t) * (size_t)n,
+                       mem == MCHB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCHB_OK;
+}
+
+// ----------------------------------------------------------------------------- rank / unrank
+int mchb_genotype_rank(mchb_handle *h, int mem, const int64_t *alleles, int64_t n, int32_t ploidy, int64_t *out_index) {
+    if (!h || !alleles || !out_index || n < 0 || ploidy < 1) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return MCHB_OK;
+    const int64_t *din;
+    int64_t *dout;
+    int rc = stage_in(h, mem, S_AUX0, alleles, n * ploidy, &din);
+    if (rc) return rc;
+    rc = stage_out(h, mem, S_AUX1, out_index, n, &dout);
+    if (rc) return rc;
+    rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(din, n, ploidy, dout);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (mem == MCHB_MEM_HOST)
+        CK(cudaMemcpyAsync(out_index, dout, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCHB_OK;
+}
+
+int mchb_genotype_unrank(mchb_handle *h, int mem, const int64_t *index, int64_t n, int32_t ploidy, int64_t *out_alleles) {
+    if (!h || !index || !out_alleles || n < 0 || ploidy < 1) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n == 0) return MCHB_OK;
+    const int64_t *din;
+    int64_t *dout;
+    int rc = stage_in(h, mem, S_AUX0, index, n, &din);
+    if (rc) return rc;
+    rc = stage_out(h, mem, S_AUX1, out_alleles, n * ploidy, &dout);
+    if (rc) return rc;
+    unrank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(din, n, ploidy, dout);
+    CK(cudaGetLastError());
+    h->launches++;
+    if (mem == MCHB_MEM_HOST)
+        CK(cudaMemcpyAsync(out_alleles, dout, sizeof(int64_t) * (size_t)n * ploidy, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MCHB_OK;
+}
+
+// ------------------------------------------------------------------------------ K1 llk batch
+int mchb_log_likelihood_batch(mchb_handle *h, int mem, const mchb_llk_item *items, int64_t n_items,
+                              const double *reads, int64_t reads_len, const int64_t *counts,
+                              int64_t counts_len, const int8_t *genotypes, int64_t genotypes_len,
+                              double *out_llk) {
+    if (!h || !items || !out_llk || n_items < 0) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_llk_item &it = items[i];
+        int64_t rsz = (int64_t)it.n_reads * it.n_pos * it.max_allele;
+        if (it.n_reads < 0 || it.n_pos < 0 || it.max_allele < 0 || it.ploidy < 0 || it.reads_off < 0 ||
+            it.reads_off + rsz > reads_len || it.geno_off < 0 ||
+            it.geno_off + (int64_t)it.ploidy * it.n_pos > genotypes_len ||
+            (counts && (it.counts_off < 0 || it.counts_off + it.n_reads > counts_len))) {
+            h->err = "llk item " + std::to_string(i) + " exceeds the given array lengths";
+            return MCHB_ERR_ARGUMENT;
+        }
+    }
+    void *ditems;
+    int rc = ensure(h, S_ITEMS, sizeof(mchb_llk_item) * (size_t)n_items, &ditems);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_llk_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    const double *dreads;
+    const int64_t *dcounts;
+    const int8_t *dgeno;
+    double *dout;
+    if ((rc = stage_in(h, mem, S_READS, reads, reads_len, &dreads))) return rc;
+    if ((rc = stage_in(h, mem, S_COUNTS, counts, counts_len, &dcounts))) return rc;
+    if ((rc = stage_in(h, mem, S_GENO, genotypes, genotypes_len, &dgeno))) return rc;
+    if ((rc = stage_out(h, mem, S_OUT_L, out_llk, n_items, &dout))) return rc;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    llk_batch_kernel<<<(unsigned)((n_items + 3) / 4), 128, 0, h->stream>>>((const mchb_llk_item *)ditems, n_items, dreads,
+                                                                            dcounts, dgeno, dout);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    if (mem == MCHB_MEM_HOST)
+        CK(cudaMemcpyAsync(out_llk, dout, sizeof(double) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->kernel_ms, h->ev0, h->ev1));
+    return MCHB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------- K2 assemble
+namespace {
+
+struct AsmGeom {
+    int nmax = 1, amax = 1, pmax = 1, tmax = 1, maxopt = 1;
+};
+
+// per-warp shared memory layout: fills the byte offsets in args, returns the region size
+size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
+    const size_t upad = (size_t)ch * 32;
+    size_t off = 0;
+    auto take = [&](size_t bytes, size_t align) {
+        off = (off + align - 1) & ~(align - 1);
+        size_t o = off;
+        off += bytes;
+        return (int32_t)o;
+    };
+    take((size_t)g.nmax * g.amax * upad * 8, 16);                      // Rt at 0
+    args.o_cnt = take(upad * 8, 8);
+    args.o_q = take((size_t)g.tmax * g.pmax * upad * 8, 8);
+    args.o_dist = take((size_t)g.nmax * g.amax * 8, 8);
+    args.o_oll = take((size_t)(g.maxopt + 1) * 8, 8);
+    args.o_opr = take((size_t)(g.maxopt + 1) * 8, 8);
+    args.o_lgdisp = take((size_t)(g.pmax + 2) * 8, 8);
+    args.o_homlp = take((size_t)g.amax * 8, 8);
+    args.o_llk_t = take((size_t)g.tmax * 8, 8);
+    args.o_key = take((size_t)g.tmax * g.pmax * 8, 8);
+    args.o_sc = take((size_t)SC_COUNT * 8, 8);
+    args.o_perm = take((size_t)g.pmax * g.nmax * 2, 2);
+    args.o_het = take((size_t)g.nmax, 1);
+    args.o_fixa = take((size_t)g.nmax, 1);
+    args.o_nall = take((size_t)g.nmax, 1);
+    args.o_opt0 = take((size_t)g.maxopt + 1, 1);
+    args.o_opt1 = take((size_t)g.maxopt + 1, 1);
+    args.o_ivb = take((size_t)g.nmax + 2, 1);
+    args.o_ivp = take((size_t)g.nmax + 2, 1);
+    return (off + 15) & ~(size_t)15;
+}
+
+template <int CH>
+int launch_assemble(mchb_handle *h, AsmArgs &args, const AsmGeom &g, int n_items_class) {
+    const size_t per_warp = asm_layout(g, CH, args);
+    int warps_per_cta = 4;
+    while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
+    if (per_warp * warps_per_cta > (size_t)h->smem_optin) {
+        h->err = "assemble item needs more shared memory than one CTA can have";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const size_t smem = per_warp * warps_per_cta;
+    CK(cudaFuncSetAttribute(assemble_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, assemble_kernel<CH>, warps_per_cta * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long want = ((long long)n_items_class + warps_per_cta - 1) / warps_per_cta;
+    long long grid = std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
+    if (grid < 1) grid = 1;
+    args.nmax = g.nmax;
+    args.amax = g.amax;
+    args.pmax = g.pmax;
+    args.tmax = g.tmax;
+    args.maxopt = g.maxopt;
+    args.smem_per_warp = (int)per_warp;
+    assemble_kernel<CH><<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(args);
+    CK(cudaGetLastError());
+    h->launches++;
+    return MCHB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *params,
+                        const mchb_assemble_item *items, int64_t n_items, const double *reads,
+                        int64_t reads_len, const int64_t *counts, int64_t counts_len,
+                        const int8_t *n_alleles, int64_t n_alleles_len, const int8_t *initial,
+                        int64_t initial_len, int8_t *out_genotypes, int64_t out_genotypes_len,
+                        double *out_llks, int64_t out_llks_len, mchb_item_result *results) {
+    if (!h || !params || !items || !results || n_items < 0 || !out_genotypes || !out_llks) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    if (n_items > 0x7fffffff) {
+        h->err = "too many items in one call";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const mchb_assemble_params &pp = *params;
+    if (pp.steps < 0 || pp.chains < 0 || !pp.break_table || !pp.break_len || pp.break_rows < 1 || !pp.temperatures) {
+        h->err = "bad assemble parameters";
+        return MCHB_ERR_ARGUMENT;
+    }
+    // ---- validate, classify by unique-read chunk count, collect seeds
+    std::vector<int32_t> order[4];  // CH = 1, 2, 4, 8
+    AsmGeom geom[4];
+    std::map<uint32_t, int32_t> seed_index;
+    std::vector<uint32_t> seeds;
+    std::vector<int32_t> item_stream((size_t)n_items, 0);
+    int64_t words_needed = 0;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_assemble_item &it = items[i];
+        const int64_t rsz = (int64_t)it.n_reads * it.n_pos * it.max_allele;
+        const int64_t gsz = (int64_t)pp.chains * pp.steps * it.ploidy * it.n_pos;
+        bool bad = it.n_reads < 0 || it.n_pos < 0 || it.max_allele < 1 || it.ploidy < 1 || it.n_temps < 1 ||
+                   it.reads_off < 0 || it.reads_off + rsz > reads_len || it.nalleles_off < 0 ||
+                   it.nalleles_off + it.n_pos > n_alleles_len || it.genotypes_off < 0 ||
+                   it.genotypes_off + gsz > out_genotypes_len || it.llks_off < 0 ||
+                   it.llks_off + (int64_t)pp.chains * pp.steps > out_llks_len || it.temps_off < 0 ||
+                   it.temps_off + it.n_temps > pp.temperatures_len ||
+                   (counts && it.n_reads > 0 && (it.counts_off < 0 || it.counts_off + it.n_reads > counts_len)) ||
+                   (initial && it.initial_off >= 0 &&
+                    it.initial_off + (int64_t)pp.chains * it.ploidy * it.initial_nhet > initial_len);
+        if (bad) {
+            h->err = "assemble item " + std::to_string(i) + " exceeds the given array lengths";
+            return MCHB_ERR_ARGUMENT;
+        }
+        results[i].status = MCHB_ITEM_OK;
+        results[i].n_het = 0;
+        results[i].rng_words = 0;
+        results[i].llk_evals = 0;
+        if (it.n_reads > 256 || it.ploidy > MCHB_MAX_PLOIDY || it.n_temps > MCHB_MAX_TEMPS || it.n_pos > 255 ||
+            it.max_allele > 255) {
+            results[i].status = MCHB_ITEM_UNSUPPORTED;
+            continue;
+        }
+        if (it.n_pos == 0) {  // nothing to sample: empty traces, NaN llks are written by the host shim
+            continue;
+        }
+        int cls = it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 128 ? 2 : 3;
+        order[cls].push_back((int32_t)i);
+        AsmGeom &g = geom[cls];
+        g.nmax = std::max(g.nmax, it.n_pos);
+        g.amax = std::max(g.amax, it.max_allele);
+        g.pmax = std::max(g.pmax, it.ploidy);
+        g.tmax = std::max(g.tmax, it.n_temps);
+        if (!pp.replay_words) {
+            auto f = seed_index.find(it.seed);
+            if (f == seed_index.end()) {
+                f = seed_index.emplace(it.seed, (int32_t)seeds.size()).first;
+                seeds.push_back(it.seed);
+            }
+            item_stream[(size_t)i] = f->second;
+        }
+        const int64_t pn = (int64_t)it.ploidy * it.n_pos;
+        const int64_t per_step = (4 * pn + 10 * (int64_t)it.n_pos + 24) * it.n_temps;
+        words_needed = std::max(words_needed, (int64_t)pp.chains * (2 * pn + 8 + (int64_t)pp.steps * per_step) + 64);
+    }
+    for (int c = 0; c < 4; c++) {
+        AsmGeom &g = geom[c];
+        g.maxopt = std::max({g.pmax * (g.pmax - 1), g.amax, (int)pp.break_stride, 2});
+    }
+    // ---- device copies of the small tables
+    void *ditems, *dstream, *dbreaks, *dbreaklen, *dtemps, *dcounter, *dresults;
+    int rc;
+    if ((rc = ensure(h, S_ITEMS, sizeof(mchb_assemble_item) * (size_t)n_items, &ditems))) return rc;
+    if ((rc = ensure(h, S_STREAM, sizeof(int32_t) * (size_t)n_items, &dstream))) return rc;
+    if ((rc = ensure(h, S_BREAKS, sizeof(double) * (size_t)pp.break_rows * pp.break_stride, &dbreaks))) return rc;
+    if ((rc = ensure(h, S_BREAKLEN, sizeof(int32_t) * (size_t)pp.break_rows, &dbreaklen))) return rc;
+    if ((rc = ensure(h, S_TEMPS, sizeof(double) * (size_t)pp.temperatures_len, &dtemps))) return rc;
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8, &dcounter))) return rc;
+    if ((rc = ensure(h, S_RESULTS, sizeof(mchb_item_result) * (size_t)n_items, &dresults))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_assemble_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dstream, item_stream.data(), sizeof(int32_t) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dbreaks, pp.break_table, sizeof(double) * (size_t)pp.break_rows * pp.break_stride,
+                       cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dbreaklen, pp.break_len, sizeof(int32_t) * (size_t)pp.break_rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dtemps, pp.temperatures, sizeof(double) * (size_t)pp.temperatures_len, cudaMemcpyHostToDevice,
+                       h->stream));
+    CK(cudaMemcpyAsync(dresults, results, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    // ---- bulk arrays
+    const double *dreads;
+    const int64_t *dcounts;
+    const int8_t *dnall, *dinit;
+    int8_t *dog;
+    double *dol;
+    if ((rc = stage_in(h, mem, S_READS, reads, reads_len, &dreads))) return rc;
+    if ((rc = stage_in(h, mem, S_COUNTS, counts, counts_len, &dcounts))) return rc;
+    if ((rc = stage_in(h, mem, S_NALLELES, n_alleles, n_alleles_len, &dnall))) return rc;
+    if ((rc = stage_in(h, mem, S_INITIAL, initial, initial_len, &dinit))) return rc;
+    if ((rc = stage_out(h, mem, S_OUT_G, out_genotypes, out_genotypes_len, &dog))) return rc;
+    if ((rc = stage_out(h, mem, S_OUT_L, out_llks, out_llks_len, &dol))) return rc;
+
+    // ---- word streams + launches (retry with longer streams if an item runs out of words)
+    int64_t stream_len = pp.rng_words_hint > 0 ? pp.rng_words_hint : words_needed;
+    if (pp.replay_words) stream_len = pp.replay_len;
+    stream_len = (stream_len + 31) & ~(int64_t)31;
+    std::vector<int32_t> todo[4];
+    for (int c = 0; c < 4; c++) todo[c] = order[c];
+    for (int attempt = 0; attempt < 6; attempt++) {
+        int64_t total = 0;
+        for (int c = 0; c < 4; c++) total += (int64_t)todo[c].size();
+        if (total == 0) break;
+        uint32_t *dwords = nullptr;
+        if (pp.replay_words) {
+            void *p;
+            if ((rc = ensure(h, S_WORDS, sizeof(uint32_t) * (size_t)stream_len, &p))) return rc;
+            CK(cudaMemsetAsync(p, 0, sizeof(uint32_t) * (size_t)stream_len, h->stream));
+            CK(cudaMemcpyAsync(p, pp.replay_words, sizeof(uint32_t) * (size_t)pp.replay_len, cudaMemcpyHostToDevice,
+                               h->stream));
+            dwords = (uint32_t *)p;
+        } else {
+            if ((rc = fill_streams(h, seeds, stream_len, &dwords))) return rc;
+        }
+        void *dorder;
+        if ((rc = ensure(h, S_ORDER, sizeof(int32_t) * (size_t)total, &dorder))) return rc;
+        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+        CK(cudaEventRecord(h->ev0, h->stream));
+        int64_t off = 0;
+        for (int c = 0; c < 4; c++) {
+            if (todo[c].empty()) continue;
+            int32_t *dord = (int32_t *)dorder + off;
+            CK(cudaMemcpyAsync(dord, todo[c].data(), sizeof(int32_t) * todo[c].size(), cudaMemcpyHostToDevice, h->stream));
+            AsmArgs args;
+            memset(&args, 0, sizeof(args));
+            args.items = (const mchb_assemble_item *)ditems;
+            args.order = dord;
+            args.n_order = (int32_t)todo[c].size();
+            args.reads = dreads;
+            args.counts = dcounts;
+            args.n_alleles = dnall;
+            args.initial = dinit;
+            args.out_genotypes = dog;
+            args.out_llks = dol;
+            args.results = (mchb_item_result *)dresults;
+            args.words = dwords;
+            args.item_stream = (const int32_t *)dstream;
+            args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
+            args.steps = pp.steps;
+            args.chains = pp.chains;
+            args.fix_homozygous = pp.fix_homozygous;
+            args.p_recomb = pp.p_recombination;
+            args.p_partial = pp.p_partial_dosage;
+            args.p_dosage = pp.p_dosage;
+            args.break_table = (const double *)dbreaks;
+            args.break_len = (const int32_t *)dbreaklen;
+            args.break_rows = pp.break_rows;
+            args.break_stride = pp.break_stride;
+            args.temperatures = (const double *)dtemps;
+            args.work_counter = (int32_t *)dcounter + c;
+            switch (c) {
+                case 0: rc = launch_assemble<1>(h, args, geom[c], (int)todo[c].size()); break;
+                case 1: rc = launch_assemble<2>(h, args, geom[c], (int)todo[c].size()); break;
+                case 2: rc = launch_assemble<4>(h, args, geom[c], (int)todo[c].size()); break;
+                default: rc = launch_assemble<8>(h, args, geom[c], (int)todo[c].size()); break;
+            }
+            if (rc) return rc;
+            off += (int64_t)todo[c].size();
+        }
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->kernel_ms += ms;
+        if (pp.replay_words) break;
+        // collect the items that ran out of words
+        bool again = false;
+        for (int c = 0; c < 4; c++) {
+            std::vector<int32_t> next;
+            for (int32_t id : todo[c])
+                if (results[id].status == MCHB_ITEM_RNG_EXHAUSTED) next.push_back(id);
+            todo[c].swap(next);
+            again = again || !todo[c].empty();
+        }
+        if (!again) break;
+        stream_len *= 2;
+    }
+    if (mem == MCHB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_genotypes, dog, (size_t)out_genotypes_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_llks, dol, sizeof(double) * (size_t)out_llks_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return MCHB_OK;
+}
+
+}  // extern "C"

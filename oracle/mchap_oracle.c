@@ -1163,6 +1163,18 @@ double orc_structural_compound_step(orc_rng *rng, int8_t *genotype, int P, int N
 /* assemble/mcmc.py                                                           */
 /* ------------------------------------------------------------------------- */
 
+/* assemble/mcmc.py:294 `np.log(n_alleles).sum()` with n_alleles an int8 array: numba resolves
+ * the ufunc loop to float32 (int8 -> 'f'), and ndarray.sum() accumulates in the array dtype,
+ * so the reference's log_unique_haplotypes is a float32 quantity (verified against numba;
+ * fixture luh_*). */
+double orc_log_unique_haplotypes(const int8_t *n_alleles, int N)
+{
+    float s = 0.0f;
+    for (int j = 0; j < N; j++)
+        s += logf((float)n_alleles[j]);
+    return (double)s;
+}
+
 /* assemble/mcmc.py:269-426 _denovo_assembler (return_heated_trace=False).
  * genotype int8[P,N] initial state (not modified); n_alleles int8[N];
  * break_dist f64[n_break_dist]; temperatures ascending f64[T];
@@ -1175,9 +1187,7 @@ int orc_denovo_assembler(orc_rng *rng, const int8_t *genotype, int P, int N, con
                          double *out_llks, int64_t *out_llk_evals)
 {
     asm_ctx c;
-    double log_unique_haplotypes = 0.0;
-    for (int j = 0; j < N; j++)
-        log_unique_haplotypes += log((double)n_alleles[j]); /* mcmc.py:294 */
+    double log_unique_haplotypes = orc_log_unique_haplotypes(n_alleles, N); /* mcmc.py:294 */
     ctx_init(&c, reads, U, N, A, counts, P, inbreeding, log_unique_haplotypes);
     size_t gsz = (size_t)P * N;
     int8_t *genotypes = (int8_t *)malloc(gsz * (size_t)T + 1);

@@ -147,6 +147,8 @@ def lib():
             C.c_double, C.c_int, _f64p, C.c_int, C.c_double, C.c_double, C.c_double, _f64p,
             C.c_int, _i8p, _f64p, _i64p,
         ]
+        L.orc_log_unique_haplotypes.restype = C.c_double
+        L.orc_log_unique_haplotypes.argtypes = [_i8p, C.c_int]
         L.orc_homozygosity_probabilities.argtypes = [
             _f64p, C.c_int, C.c_int, C.c_int, _i8p, C.c_int, C.c_double, _i64p, _f64p,
         ]
@@ -595,6 +597,12 @@ def denovo_assembler(rng, genotype, reads, n_alleles, steps, break_dist, inbreed
     )
     _raise(err)
     return og, ol, ev.value
+
+
+def log_unique_haplotypes(n_alleles):
+    """assemble/mcmc.py:294 (float32 arithmetic, see mchap_oracle.c)"""
+    na = _i8(n_alleles)
+    return lib().orc_log_unique_haplotypes(_p(na, _i8p), len(na))
 
 
 def homozygosity_probabilities(reads, n_alleles, ploidy, inbreeding=None, read_counts=None):

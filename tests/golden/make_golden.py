@@ -95,6 +95,20 @@ def _rng_probe(seed):
     return out
 
 
+@numba.njit
+def _luh(n_alleles):
+    return np.log(n_alleles).sum()
+
+
+def luh_cases():
+    arrs = [[2] * 8, [2, 3, 4, 2], [4] * 16, [2], [3, 3, 3, 2, 2, 4, 4, 2, 2, 2, 3]]
+    for k, a in enumerate(arrs):
+        a = np.array(a, dtype=np.int8)
+        OUT["luh%d_in" % k] = a
+        OUT["luh%d_out" % k] = np.array([_luh(a)], dtype=np.float64)
+    META["luh_cases"] = len(arrs)
+
+
 def rng_cases():
     for seed in (0, 11, 42, 123456789):
         OUT["rng_probe_%d" % seed] = _rng_probe(seed)
@@ -553,6 +567,7 @@ def exact_cases():
 
 def main():
     rng_cases()
+    luh_cases()
     likelihood_cases()
     jitutils_cases()
     prior_cases()

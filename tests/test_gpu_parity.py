@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the C oracle on the same seeded
+inputs, and against the committed reference fixtures.
+
+Bars (BASELINE.json north_star): integers / indices / trajectories bit-exact; fp64
+log-likelihoods within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LLK_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import mchap_b200
+
+    return mchap_b200.default_device(0)
+
+
+def close(a, b, rtol=LLK_RTOL):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=0, equal_nan=True)
+
+
+def test_native_library_is_loaded(dev):
+    import mchap_b200._lib as L
+
+    with open("/proc/self/maps") as f:
+        assert "libmchap_b200.so" in f.read()
+    assert dev.sm_count > 0
+    assert L.library_path().endswith("libmchap_b200.so")
+
+
+def test_mt19937_stream(dev, oracle):
+    for seed, n in ((0, 1), (11, 623), (42, 624), (42, 5000), (123456789, 70001)):
+        np.testing.assert_array_equal(dev.mt19937_words(seed, n), oracle.mt19937_words(seed, n))
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 6, 8])
+def test_rank_unrank_bit_exact(dev, golden, P):
+    un = golden["unrank_p%d" % P]
+    idx = np.arange(len(un), dtype=np.int64)
+    np.testing.assert_array_equal(dev.index_as_genotype_alleles(idx, P), un)
+    np.testing.assert_array_equal(dev.genotype_alleles_as_index(un), idx)
+
+
+def test_rank_unrank_large_and_negative(dev, golden):
+    idx = golden["unrank_large_idx"]
+    got = dev.index_as_genotype_alleles(idx, 6)
+    np.testing.assert_array_equal(got, golden["unrank_large_p6"])
+    np.testing.assert_array_equal(dev.genotype_alleles_as_index(got), idx)
+    assert (dev.index_as_genotype_alleles(np.array([-1]), 4) == -1).all()
+    # a round trip at full enumeration size: all 52360 tetraploid genotypes of 32 haplotypes
+    allidx = np.arange(52360, dtype=np.int64)
+    g = dev.index_as_genotype_alleles(allidx, 4)
+    assert (np.diff(g, axis=1) >= 0).all() and g.max() == 31
+    np.testing.assert_array_equal(dev.genotype_alleles_as_index(g), allidx)
+
+
+def test_log_likelihood_golden(dev, golden):
+    ks = golden.meta["llk_cases"]
+    reads = [golden["llk%d_reads" % k] for k in ks]
+    genos = [golden["llk%d_genotype" % k] for k in ks]
+    counts = [golden.get("llk%d_counts" % k) for k in ks]
+    got = dev.log_likelihood_batch(reads, genos, counts)
+    want = np.array([golden["llk%d_out" % k][0] for k in ks])
+    close(got, want)
+    # structural-change llk == llk of the changed genotype
+    changed = [golden["llk%d_changed" % k] for k in ks]
+    got2 = dev.log_likelihood_batch(reads, changed, counts)
+    close(got2, np.array([golden["llk%d_out" % k][1] for k in ks]))
+
+
+def test_log_likelihood_vs_oracle_fuzz(dev, oracle):
+    rng = np.random.default_rng(3)
+    reads, genos, counts, want = [], [], [], []
+    for _ in range(200):
+        P, N, A, U = int(rng.integers(1, 9)), int(rng.integers(1, 17)), int(rng.integers(2, 5)), int(rng.integers(1, 90))
+        r = rng.random((U, N, A))
+        r[rng.random((U, N)) < 0.3] = np.nan
+        g = rng.integers(0, A, size=(P, N)).astype(np.int8)
+        c = rng.integers(1, 9, size=U)
+        reads.append(r)
+        genos.append(g)
+        counts.append(c)
+        want.append(oracle.log_likelihood(r, g, c))
+    close(dev.log_likelihood_batch(reads, genos, counts), np.array(want), rtol=1e-12)
+
+
+def _fit_model(meta, na):
+    from mchap_b200 import DenovoMCMC
+
+    return DenovoMCMC(
+        ploidy=meta["P"], n_alleles=list(na), inbreeding=meta["inbreeding"], steps=meta["steps"],
+        chains=meta["chains"], n_intervals=meta["n_intervals"], fix_homozygous=meta["fix_homozygous"],
+        recombination_step_probability=meta["probs"][0], partial_dosage_step_probability=meta["probs"][1],
+        dosage_step_probability=meta["probs"][2], temperatures=tuple(meta["temperatures"]),
+        random_seed=meta["seed"])
+
+
+def test_denovo_fit_golden_trajectories(dev, golden, oracle):
+    """Reference fixtures: step-for-step identical genotype traces, llks to 1e-9, and the same
+    number of MT19937 words consumed as numba."""
+    for k in range(golden.meta["fit_cases"]):
+        meta = golden.meta["fit%d" % k]
+        reads = golden["fit%d_reads" % k]
+        counts = golden.get("fit%d_counts" % k)
+        na = golden["fit%d_nalleles" % k]
+        model = _fit_model(meta, na)
+        (res,), results = model.fit_batch([reads], [counts], return_results=True, raw=True)
+        g, l = res
+        if meta.get("edge"):
+            from mchap_b200.assemble.classes import sort_haplotypes
+
+            np.testing.assert_array_equal(sort_haplotypes(g), golden["fit%d_sorted" % k], err_msg="case %d" % k)
+            close(l, golden["fit%d_llks" % k])
+            continue
+        np.testing.assert_array_equal(g, golden["fit%d_genotypes" % k], err_msg="case %d" % k)
+        close(l, golden["fit%d_llks" % k])
+        assert results["n_het"][0] == golden["fit%d_nhet" % k][0]
+        # RNG position: the next double numba would draw after the fit
+        r = oracle.Rng(meta["seed"])
+        for _ in range(int(results["rng_words"][0])):
+            r.u32()
+        assert r.random() == golden["fit%d_next" % k][0]
+        # the public fit() returns the sorted trace of the reference
+        trace = model.fit(reads, read_counts=counts)
+        np.testing.assert_array_equal(trace.genotypes, golden["fit%d_sorted" % k])
+
+
+def _oracle_fit(oracle, model, reads, counts, na, seed=None, replay=None):
+    return oracle.denovo_fit(
+        reads, counts, model.ploidy, na, inbreeding=model.inbreeding, steps=model.steps, chains=model.chains,
+        alpha=model.alpha, beta=model.beta, n_intervals=model.n_intervals, fix_homozygous=model.fix_homozygous,
+        recombination_step_probability=model.recombination_step_probability,
+        partial_dosage_step_probability=model.partial_dosage_step_probability,
+        dosage_step_probability=model.dosage_step_probability, temperatures=model.temperatures,
+        random_seed=model.random_seed if seed is None else seed, replay_words=replay)
+
+
+@pytest.mark.parametrize("ploidy,n_pos,depth,temps,inbreeding", [
+    (4, 8, 40, (1.0,), None),          # BASELINE configs[1] shape
+    (4, 8, 40, (1.0,), 0.1),
+    (2, 6, 20, (1.0,), None),
+    (6, 8, 40, (0.2, 1.0), None),
+    (8, 16, 100, (0.01, 0.1, 0.5, 1.0), None),   # BASELINE configs[3] shape
+    (4, 12, 60, (0.5, 1.0), 0.3),
+])
+def test_assemble_batch_vs_oracle(dev, oracle, ploidy, n_pos, depth, temps, inbreeding):
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.synth import synth_items
+
+    n_items = 24
+    steps = 120 if n_pos <= 8 else 40
+    batch = synth_items(n_items, ploidy=ploidy, n_pos=n_pos, depth=depth, seed=ploidy * 100 + n_pos)
+    model = DenovoMCMC(ploidy=ploidy, n_alleles=[2] * n_pos, inbreeding=inbreeding, steps=steps, chains=2,
+                       temperatures=temps, random_seed=11)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    out, results = model.fit_batch(reads, counts, return_results=True, raw=True)
+    total_evals = 0
+    for i in range(n_items):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], [2] * n_pos)
+        g, l = out[i]
+        np.testing.assert_array_equal(g, ref["genotypes"], err_msg="item %d" % i)
+        close(l, ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+        assert results["n_het"][i] == ref["n_het"]
+        assert results["llk_evals"][i] == ref["llk_evals"]
+        total_evals += ref["llk_evals"]
+    assert total_evals > 0
+
+
+def test_assemble_per_item_seeds_and_ragged_alleles(dev, oracle):
+    from mchap_b200 import DenovoMCMC
+
+    rng = np.random.default_rng(5)
+    reads, counts, nalls, seeds = [], [], [], []
+    for i in range(12):
+        N = int(rng.integers(2, 9))
+        A = 4
+        na = rng.integers(2, A + 1, size=N).astype(np.int8)
+        U = int(rng.integers(3, 45))
+        r = rng.random((U, N, A)) + 0.05
+        for j in range(N):
+            r[:, j, na[j]:] = 0
+        r /= r.sum(axis=-1, keepdims=True)
+        r[rng.random((U, N)) < 0.25] = np.nan
+        reads.append(r)
+        counts.append(rng.integers(1, 5, size=U))
+        nalls.append(na)
+        seeds.append(int(rng.integers(0, 2 ** 31)))
+    model = DenovoMCMC(ploidy=4, n_alleles=None, inbreeding=0.05, steps=60, chains=2, random_seed=1)
+    out, results = model.fit_batch(reads, counts, n_alleles_list=nalls, seeds=seeds, return_results=True, raw=True)
+    for i in range(12):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], nalls[i], seed=seeds[i])
+        np.testing.assert_array_equal(out[i][0], ref["genotypes"], err_msg="item %d" % i)
+        close(out[i][1], ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+
+
+def test_replay_harness(dev, oracle):
+    """Both implementations driven by the same pre-drawn word stream (not an MT19937 stream)."""
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.synth import synth_items
+
+    batch = synth_items(4, seed=99)
+    words = np.random.default_rng(7).integers(0, 2 ** 32, size=200000, dtype=np.uint64).astype(np.uint32)
+    model = DenovoMCMC(ploidy=4, n_alleles=[2] * 8, steps=100, chains=2, random_seed=0)
+    reads = [batch.item(i)[0] for i in range(4)]
+    counts = [batch.item(i)[1] for i in range(4)]
+    out = model.fit_batch(reads, counts, raw=True, replay_words=words)
+    for i in range(4):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], [2] * 8, replay=words)
+        np.testing.assert_array_equal(out[i][0], ref["genotypes"])
+        close(out[i][1], ref["llks"])
+
+
+def test_edge_cases(dev):
+    from mchap_b200 import DenovoMCMC
+
+    # zero reads (tests/test_assemble/test_mcmc.py:95-111): a random walk, must run and be seeded
+    model = DenovoMCMC(ploidy=4, n_alleles=[2, 2, 2], steps=50, chains=2, random_seed=3)
+    t1 = model.fit(np.empty((0, 3, 2)))
+    t2 = model.fit(np.empty((0, 3, 2)))
+    np.testing.assert_array_equal(t1.genotypes, t2.genotypes)
+    assert t1.genotypes.shape == (2, 50, 4, 3)
+    # zero SNPs (114-149)
+    t = DenovoMCMC(ploidy=4, n_alleles=[], steps=20, chains=2, random_seed=3).fit(np.empty((5, 0, 0)))
+    assert t.genotypes.shape == (2, 20, 4, 0) and np.isnan(t.llks).all()
+    # unsupported shape fails loudly instead of falling back
+    with pytest.raises(NotImplementedError):
+        DenovoMCMC(ploidy=2, n_alleles=[2] * 70, steps=5, chains=1, random_seed=1, fix_homozygous=2.0).fit(
+            np.full((3, 70, 2), 0.5))

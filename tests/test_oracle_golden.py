@@ -42,6 +42,12 @@ def test_mt19937_words_equal_numpy_legacy(oracle):
         np.testing.assert_array_equal(w, ref)
 
 
+def test_log_unique_haplotypes_is_float32(golden, oracle):
+    # assemble/mcmc.py:294: numba evaluates np.log(int8 array).sum() in float32
+    for k in range(golden.meta["luh_cases"]):
+        assert oracle.log_unique_haplotypes(golden["luh%d_in" % k]) == golden["luh%d_out" % k][0]
+
+
 def test_log_likelihood(golden, oracle):
     for k in golden.meta["llk_cases"]:
         reads = golden["llk%d_reads" % k]
