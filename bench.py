@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py — locus x sample MCMC steps/s of the assemble hot path (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torchrun)
+    python bench.py --impl reference ...                    (CPU arm: the oracle port, all host cores)
+
+Workload (config.workload): synthetic tetraploid assemble, 10k loci x 8 SNVs x 100 samples,
+depth 40, 2 chains x 1500 MCMC steps, flat prior, CLI-default step probabilities, seed shared by
+all items like the CLI (mchap/application/assemble.py:135).  The K timed bench steps are K batches
+that together cover the 10 000 loci once (a bench "step" = one pass of the hot path over one batch
+of 10000/K loci x 100 samples).  With N GPUs every rank runs its own 10k-locus workload (weak
+scaling, no collective on the data path; loci are independent).
+
+JSON keys follow the round contract: value (device-resident throughput, CUDA events, max over
+ranks), e2e (host buffers through the C ABI, H2D + D2H inside the timed region), roofline
+(FP64 SIMT pipe: algorithmic flops of SURVEY.md section 8(d) / kernel time, against a DFMA
+probe measured live), cpu_baseline (C oracle on the host cores, bounded sample), clocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PLOIDY, N_POS, DEPTH, SAMPLES, LOCI = 4, 8, 40, 100, 10000
+CHAINS, MCMC_STEPS, SEED = 2, 1500, 42
+METRIC = "locus x sample MCMC steps/s (assemble)"
+UNIT = "MCMC steps/s"
+WORKLOAD = ("synthetic tetraploid assemble: 10k loci x 8 SNVs x 100 samples, depth 40, "
+            "2 chains x 1500 steps")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--loci", type=int, default=LOCI, help="loci covered by the K timed steps (default: the full config)")
+    ap.add_argument("--cpu-items", type=int, default=0, help="items of the CPU baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rate(n_items, cores, seed=12345):
+    """C oracle (oracle/mchap_oracle.c: a port of the reference's numba path) over `cores`
+    threads, items split like the reference's --cores scheme (np.array_split)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from mchap_b200.synth import synth_items
+    from oracle import oracle as o
+
+    o.lib()
+    batch = synth_items(n_items, ploidy=PLOIDY, n_pos=N_POS, depth=DEPTH, seed=seed)
+    items = [batch.item(i) for i in range(n_items)]
+
+    def work(idx):
+        for i in idx:
+            r, c = items[i]
+            o.denovo_fit(r, c, PLOIDY, [2] * N_POS, steps=MCMC_STEPS, chains=CHAINS, random_seed=SEED)
+        return len(idx)
+
+    o.denovo_fit(items[0][0], items[0][1], PLOIDY, [2] * N_POS, steps=10, chains=1, random_seed=SEED)
+    parts = [p for p in np.array_split(np.arange(n_items), cores) if len(p)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        done = sum(ex.map(work, parts))
+    dt = time.perf_counter() - t0
+    return done * CHAINS * MCMC_STEPS / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_items = args.cpu_items or 6 * cores
+    vals = []
+    for _ in range(args.warmup):
+        cpu_oracle_rate(max(cores, n_items // 4), cores)
+    t_all = 0.0
+    for k in range(args.steps):
+        v, dt = cpu_oracle_rate(n_items, cores, seed=1000 + k)
+        vals.append(v)
+        t_all += dt
+    value = n_items * CHAINS * MCMC_STEPS * args.steps / t_all
+    sample = "%d locus x sample items per step (of the 1e6 of the config), %d threads" % (n_items, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "ploidy": PLOIDY, "n_pos": N_POS, "depth": DEPTH,
+                   "chains": CHAINS, "mcmc_steps": MCMC_STEPS, "items_per_step": n_items},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def algorithmic_flops(results, n_reads):
+    """one llk evaluation = U * (P*N + 2P + 3) flop with N = positions passed to
+    the sampler (n_het); the kernel reports evaluations and n_het per item."""
+    n_het = results["n_het"].astype(np.float64)
+    w = n_reads.astype(np.float64) * (PLOIDY * n_het + 2 * PLOIDY + 3)
+    return float((results["llk_evals"].astype(np.float64) * w).sum())
+
+
+def run_b200(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import mchap_b200
+    from mchap_b200 import _lib as L
+    from mchap_b200.api import make_assemble_params, uniform_assemble_items
+    from mchap_b200.assemble.mcmc import break_table
+    from mchap_b200.synth import synth_items
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = mchap_b200.Device(local)
+    gpu = torch.device("cuda", local)
+
+    K, W = args.steps, args.warmup
+    loci_per_step = -(-args.loci // K)
+    items_per_step = loci_per_step * SAMPLES
+    table, lens = break_table(N_POS)
+    params, keep = make_assemble_params(MCMC_STEPS, CHAINS, 0.999, 0.5, 0.5, 1.0, table, lens, [1.0])
+
+    # ---- synthetic inputs, one batch per timed step (distinct items; warm-up reuses batch 0..)
+    batches = []
+    for k in range(K):
+        b = synth_items(items_per_step, ploidy=PLOIDY, n_pos=N_POS, depth=DEPTH, seed=100003 * rank + k)
+        items = uniform_assemble_items(b.offsets, N_POS, b.max_allele, PLOIDY, CHAINS, MCMC_STEPS, seed=SEED)
+        batches.append((b, items))
+    g_len = items_per_step * CHAINS * MCMC_STEPS * PLOIDY * N_POS
+    l_len = items_per_step * CHAINS * MCMC_STEPS
+    d_out_g = torch.empty(g_len, dtype=torch.int8, device=gpu)
+    d_out_l = torch.empty(l_len, dtype=torch.float64, device=gpu)
+    dev_in = []
+    for b, items in batches:
+        dev_in.append((torch.from_numpy(b.reads.reshape(-1)).to(gpu), torch.from_numpy(b.counts).to(gpu),
+                       torch.from_numpy(b.n_alleles.reshape(-1)).to(gpu)))
+    torch.cuda.synchronize()
+
+    def device_step(k):
+        b, items = batches[k]
+        dr, dc, dn = dev_in[k]
+        res = dev.assemble_call(items, params, dr.data_ptr(), dc.data_ptr(), dn.data_ptr(), None,
+                                d_out_g.data_ptr(), d_out_l.data_ptr(),
+                                (dr.numel(), dc.numel(), dn.numel(), 0, g_len, l_len), mem=L.MEM_DEVICE)
+        return res, dev.last_kernel_ms, dev.last_kernel_launches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, device time by CUDA events on the launching stream.
+    # Between timed steps the kernel writes a fresh 9.6 GB trace (>> 126 MB L2) and reads a
+    # different batch, so no step finds its inputs in L2.
+    for k in range(W):
+        device_step(k % K)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    kernel_ms, launches, flops, evals = [], 0, 0.0, 0
+    t0 = time.perf_counter()
+    for k in range(K):
+        res, ms, nl = device_step(k)
+        if (res["status"] != 0).any():
+            raise RuntimeError("device reported item errors: %s" % np.unique(res["status"]))
+        kernel_ms.append(ms)
+        launches += nl
+        flops += algorithmic_flops(res, batches[k][0].n_reads())
+        evals += int(res["llk_evals"].sum())
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dev_time = sum(kernel_ms) * 1e-3
+    t = torch.tensor([dev_time, wall], dtype=torch.float64, device=gpu)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_time_max, wall_max = float(t[0]), float(t[1])
+    total_mcmc_steps = world * K * items_per_step * CHAINS * MCMC_STEPS
+    value = total_mcmc_steps / dev_time_max
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        b, items = batches[0]
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_reads, h_counts, h_nall = pin(b.reads.reshape(-1)), pin(b.counts), pin(b.n_alleles.reshape(-1))
+        h_out_g = torch.empty(g_len, dtype=torch.int8).pin_memory()
+        h_out_l = torch.empty(l_len, dtype=torch.float64).pin_memory()
+
+        def host_step():
+            return dev.assemble_call(items, params, h_reads.numpy(), h_counts.numpy(), h_nall.numpy(), None,
+                                     h_out_g.numpy(), h_out_l.numpy(),
+                                     (h_reads.numel(), h_counts.numel(), h_nall.numel(), 0, g_len, l_len),
+                                     mem=L.MEM_HOST)
+
+        host_step()
+        n_e2e = min(K, 3)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            host_step()
+            launches_e2e = dev.last_kernel_launches
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=gpu)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": world * n_e2e * items_per_step * CHAINS * MCMC_STEPS / float(t[0]), "unit": UNIT,
+            "h2d_bytes_per_step": int(h_reads.numel() * 8 + h_counts.numel() * 8 + h_nall.numel() + items.nbytes),
+            "d2h_bytes_per_step": int(g_len + l_len * 8 + items_per_step * 24),
+            "steps": n_e2e, "note": "one handle, serial H2D -> kernels -> D2H of the full trace",
+        }
+
+    # ---- roofline of the dominant kernel (assemble_kernel): FP64 SIMT pipe
+    peak_tf = dev.measure_fp64_peak()
+    achieved_tf = flops / dev_time / 1e12
+    in_bytes = sum(x[0].numel() * 8 + x[1].numel() * 8 for x in dev_in) / K
+    out_bytes = g_len + l_len * 8
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    roofline = {
+        "bound": "fp64_simt", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+        "peak_source": "DFMA probe kernel measured live in this run (MEASURED_PEAKS.json holds no FP64 figure)",
+        "kernel": "assemble_kernel<1>", "llk_evals_per_mcmc_step": evals / (K * items_per_step * CHAINS * MCMC_STEPS),
+        "hbm_achieved_gbs": (in_bytes + out_bytes) / (dev_time / K) / 1e9,
+        "hbm_peak_gbs": hbm_peak if hbm_peak else 6650.0,
+        "hbm_peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback",
+    }
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_cpu = args.cpu_items or 6 * cores
+        v, dt = cpu_oracle_rate(n_cpu, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d of the %d locus x sample items of the workload, %.1f s" % (n_cpu, LOCI * SAMPLES, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * dev_time_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ploidy": PLOIDY, "n_pos": N_POS, "depth": DEPTH, "samples": SAMPLES,
+                       "loci_per_step": loci_per_step, "loci_timed": loci_per_step * K, "chains": CHAINS,
+                       "mcmc_steps": MCMC_STEPS, "seed": SEED, "prior": "flat",
+                       "l2": "each step reads a different batch and writes a 9.6 GB trace (> L2)",
+                       "mean_unique_reads": float(np.mean([b.n_reads().mean() for b, _ in batches]))},
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "wall_ms_per_step": 1e3 * wall_max / K,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

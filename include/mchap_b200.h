@@ -76,6 +76,11 @@ int32_t mchb_last_kernel_launches(const mchb_handle *h);
 void *mchb_stream(const mchb_handle *h);
 int mchb_sm_count(const mchb_handle *h);
 
+/* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
+ * TFLOP/s from a register-resident DFMA loop; the roofline denominator for the FP64-SIMT-bound
+ * MCMC kernels. */
+int mchb_measure_fp64_peak(mchb_handle *h, double *out_tflops);
+
 /* ---- RNG: numba's np.random MT19937 stream -------------------------------------------
  * Replaces: numba's thread-local generator as the reference drives it (jitutils.py:180-183
  * seed_numba; numba/cpython/randomimpl.py get_next_int32).  Fills `out` (n words, space `mem`)

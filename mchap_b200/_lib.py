@@ -119,7 +119,7 @@ SYMBOLS = [
     "mchb_create", "mchb_destroy", "mchb_last_error", "mchb_get_limits", "mchb_last_kernel_ms",
     "mchb_last_kernel_launches", "mchb_stream", "mchb_sm_count", "mchb_mt19937_words",
     "mchb_genotype_rank", "mchb_genotype_unrank", "mchb_log_likelihood_batch",
-    "mchb_assemble_batch",
+    "mchb_assemble_batch", "mchb_measure_fp64_peak",
 ]
 
 
@@ -154,6 +154,8 @@ def load():
         L.mchb_stream.argtypes = [vp]
         L.mchb_sm_count.restype = C.c_int
         L.mchb_sm_count.argtypes = [vp]
+        L.mchb_measure_fp64_peak.restype = C.c_int
+        L.mchb_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.mchb_mt19937_words.restype = C.c_int
         L.mchb_mt19937_words.argtypes = [vp, C.c_int, C.c_uint32, vp, C.c_int64]
         L.mchb_genotype_rank.restype = C.c_int

@@ -99,6 +99,12 @@ class Device:
         L.load().mchb_get_limits(C.byref(lim))
         return {f[0]: getattr(lim, f[0]) for f in lim._fields_}
 
+    def measure_fp64_peak(self):
+        """Sustained FP64 FMA TFLOP/s of this device (register-resident DFMA loop)."""
+        out = C.c_double(0)
+        self._check(self._lib.mchb_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
+
     # ------------------------------------------------------------------ RNG / ranking
     def mt19937_words(self, seed, n):
         """numba's MT19937 output stream after np.random.seed(seed) (jitutils.py:180-183)."""
@@ -192,6 +198,31 @@ def make_assemble_params(steps, chains, fix_homozygous, p_recombination, p_parti
     p.replay_len = 0 if rw is None else rw.size
     p.rng_words_hint = int(rng_words_hint)
     return p, (bt, bl, tp, rw)
+
+
+def uniform_assemble_items(offsets, n_pos, max_allele, ploidy, chains, steps, n_temps=1, seed=42,
+                           inbreeding=None):
+    """Vectorised descriptors for a batch whose items share n_pos / max_allele / ploidy and whose
+    reads are packed back to back (``offsets`` in reads, int64[n+1]); outputs are dense per item."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
+    idx = np.arange(n, dtype=np.int64)
+    items["reads_off"] = offsets[:-1] * (n_pos * max_allele)
+    items["counts_off"] = offsets[:-1]
+    items["nalleles_off"] = idx * n_pos
+    items["initial_off"] = -1
+    items["genotypes_off"] = idx * (chains * steps * ploidy * n_pos)
+    items["llks_off"] = idx * (chains * steps)
+    items["n_reads"] = np.diff(offsets)
+    items["n_pos"] = n_pos
+    items["max_allele"] = max_allele
+    items["ploidy"] = ploidy
+    items["temps_off"] = 0
+    items["n_temps"] = n_temps
+    items["seed"] = np.uint32(seed)
+    items["inbreeding"] = np.nan if inbreeding is None else float(inbreeding)
+    return items
 
 
 _default_devices = {}

@@ -142,4 +142,23 @@ __global__ void unrank_kernel(const int64_t *index, int64_t n, int ploidy, int64
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// FP64 SIMT pipe probe: 8 independent DFMA chains per thread.  Used by bench.py to measure the
+// roofline denominator of the (FP64-bound) MCMC kernels live on the device under test.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double x, double y) {
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, x, y);
+        a1 = fma(a1, x, y);
+        a2 = fma(a2, x, y);
+        a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y);
+        a5 = fma(a5, x, y);
+        a6 = fma(a6, x, y);
+        a7 = fma(a7, x, y);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 }  // namespace mchb

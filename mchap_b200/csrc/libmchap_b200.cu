@@ -211,6 +211,32 @@ int mchb_mt19937_words(mchb_handle *h, int mem, uint32_t seed, uint32_t *out, in
     return MCHB_OK;
 }
 
+// --------------------------------------------------------------------------- FP64 pipe probe
+int mchb_measure_fp64_peak(mchb_handle *h, double *out_tflops) {
+    if (!h || !out_tflops) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    const int threads = 256, blocks = h->sm_count * 8, iters = 1 << 15;
+    void *p;
+    int rc = ensure(h, S_AUX0, sizeof(double) * (size_t)threads * blocks, &p);
+    if (rc) return rc;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(h->ev0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>((double *)p, iters, 1.0000001, 1e-9);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->launches++;
+        if (rep > 0 && ms < best) best = ms;
+    }
+    h->kernel_ms = best;
+    *out_tflops = (double)threads * blocks * (double)iters * 8.0 * 2.0 / ((double)best * 1e-3) / 1e12;
+    return MCHB_OK;
+}
+
 // ----------------------------------------------------------------------------- rank / unrank
 int mchb_genotype_rank(mchb_handle *h, int mem, const int64_t *alleles, int64_t n, int32_t ploidy, int64_t *out_index) {
     if (!h || !alleles || !out_index || n < 0 || ploidy < 1) return MCHB_ERR_ARGUMENT;
