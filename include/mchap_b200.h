@@ -164,6 +164,54 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                         int64_t initial_len, int8_t *out_genotypes, int64_t out_genotypes_len,
                         double *out_llks, int64_t out_llks_len, mchb_item_result *results);
 
+
+/* ---- exhaustive genotype calling over known haplotypes (mchap call-exact) ----------------
+ * Item i: reads f64[U,N,A], counts i64[U] (or none), haplotypes int8[H,N] in VCF allele order,
+ * optional prior = (inbreeding, frequencies f64[H] or flat).  G = C(H+P-1, P) genotypes are
+ * enumerated in VCF order (jitutils.py:113-146). */
+typedef struct {
+    int64_t reads_off;       /* doubles */
+    int64_t counts_off;      /* int64 elements; ignored if counts == NULL */
+    int64_t haps_off;        /* int8 elements: haplotypes[H, N] */
+    int64_t freqs_off;       /* doubles: prior allele frequencies [H]; -1: flat frequencies (None) */
+    int64_t hap_out_off;     /* element offset of the item's [H] row in per-haplotype outputs */
+    int64_t gl_off;          /* element offset of the item's [G] row in per-genotype arrays */
+    int32_t n_reads, n_pos, max_allele, ploidy, n_haps;
+    int32_t reserved;
+    double inbreeding;       /* NaN: prior None */
+} mchb_call_item;
+
+/* Replaces: calling/exact.py:156-249 posterior_mode with every optional result
+ * (17-61 _call_posterior_mode, 64-105 _genotype_support_log_joint, 108-153
+ * _posterior_allele_frequencies), all in float64 like the reference's low-memory branch.
+ * out_alleles i64[n_items, pstride] (mode alleles, sorted; unused slots -2);
+ * out_stats f64[n_items, 4] = mode llk, mode probability, support probability, log normaliser;
+ * out_freqs / out_occur f64 rows at hap_out_off (posterior mean allele frequencies, occurrence). */
+int mchb_call_exact_mode_batch(mchb_handle *h, int mem, const mchb_call_item *items, int64_t n_items,
+                               const double *reads, int64_t reads_len, const int64_t *counts,
+                               int64_t counts_len, const int8_t *haplotypes, int64_t haplotypes_len,
+                               const double *freqs, int64_t freqs_len, int64_t *out_alleles,
+                               int32_t pstride, double *out_stats, double *out_freqs,
+                               double *out_occur, int64_t hap_out_len, mchb_item_result *results);
+
+/* Replaces: calling/exact.py:252-292 genotype_likelihoods — float32[G] per item at gl_off, like
+ * the reference (exact.py:254). */
+int mchb_genotype_likelihoods_batch(mchb_handle *h, int mem, const mchb_call_item *items,
+                                    int64_t n_items, const double *reads, int64_t reads_len,
+                                    const int64_t *counts, int64_t counts_len,
+                                    const int8_t *haplotypes, int64_t haplotypes_len, float *out_gl,
+                                    int64_t gl_len, mchb_item_result *results);
+
+/* Replaces: calling/exact.py:295-329 genotype_posteriors (+ 332-369
+ * posterior_allele_frequencies when out_freqs != NULL).  llks: float32 (llk_is_f32 != 0; the
+ * sum llk + log-prior is rounded to float32 before the float64 normalisation exactly as numba
+ * does for a float32 input array) or float64.  out_gp f64[G] rows at gl_off. */
+int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item *items,
+                                   int64_t n_items, const double *freqs, int64_t freqs_len,
+                                   const void *llks, int llk_is_f32, int64_t gl_len, double *out_gp,
+                                   double *out_freqs, double *out_counts, double *out_occur,
+                                   int64_t hap_out_len);
+
 #ifdef __cplusplus
 }
 #endif

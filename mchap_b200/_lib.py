@@ -77,6 +77,24 @@ class AssembleItem(C.Structure):
     ]
 
 
+class CallItem(C.Structure):
+    _fields_ = [
+        ("reads_off", C.c_int64),
+        ("counts_off", C.c_int64),
+        ("haps_off", C.c_int64),
+        ("freqs_off", C.c_int64),
+        ("hap_out_off", C.c_int64),
+        ("gl_off", C.c_int64),
+        ("n_reads", C.c_int32),
+        ("n_pos", C.c_int32),
+        ("max_allele", C.c_int32),
+        ("ploidy", C.c_int32),
+        ("n_haps", C.c_int32),
+        ("reserved", C.c_int32),
+        ("inbreeding", C.c_double),
+    ]
+
+
 class AssembleParams(C.Structure):
     _fields_ = [
         ("steps", C.c_int32),
@@ -119,7 +137,8 @@ SYMBOLS = [
     "mchb_create", "mchb_destroy", "mchb_last_error", "mchb_get_limits", "mchb_last_kernel_ms",
     "mchb_last_kernel_launches", "mchb_stream", "mchb_sm_count", "mchb_mt19937_words",
     "mchb_genotype_rank", "mchb_genotype_unrank", "mchb_log_likelihood_batch",
-    "mchb_assemble_batch", "mchb_measure_fp64_peak",
+    "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
+    "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch",
 ]
 
 
@@ -170,6 +189,19 @@ def load():
         L.mchb_assemble_batch.argtypes = [
             vp, C.c_int, C.POINTER(AssembleParams), vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
             vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp,
+        ]
+        L.mchb_call_exact_mode_batch.restype = C.c_int
+        L.mchb_call_exact_mode_batch.argtypes = [
+            vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
+            vp, C.c_int32, vp, vp, vp, C.c_int64, vp,
+        ]
+        L.mchb_genotype_likelihoods_batch.restype = C.c_int
+        L.mchb_genotype_likelihoods_batch.argtypes = [
+            vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp,
+        ]
+        L.mchb_genotype_posteriors_batch.restype = C.c_int
+        L.mchb_genotype_posteriors_batch.argtypes = [
+            vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int64,
         ]
         _lib = L
         return _lib

@@ -12,6 +12,7 @@ from . import _lib as L
 ASSEMBLE_ITEM_DTYPE = L._np_dtype(L.AssembleItem)
 LLK_ITEM_DTYPE = L._np_dtype(L.LlkItem)
 ITEM_RESULT_DTYPE = L._np_dtype(L.ItemResult)
+CALL_ITEM_DTYPE = L._np_dtype(L.CallItem)
 
 _ITEM_ERRORS = {
     L.ITEM_NAN_LLK: (ValueError, "Encountered log likelihood of nan"),
@@ -158,6 +159,49 @@ class Device:
             0 if counts is None else counts.size, _ptr(genos), genos.size, _ptr(out)))
         return out
 
+    # ------------------------------------------------------------------ K4
+    def call_exact_mode(self, batch):
+        """calling/exact.py:156-249 for a CallBatch -> dict of arrays."""
+        n = batch.n
+        alleles = np.zeros((n, batch.pmax), dtype=np.int64)
+        stats = np.zeros((n, 4), dtype=np.float64)
+        freqs = np.zeros(max(batch.hap_total, 1), dtype=np.float64)
+        occur = np.zeros(max(batch.hap_total, 1), dtype=np.float64)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        self._check(self._lib.mchb_call_exact_mode_batch(
+            self._h, L.MEM_HOST, _ptr(batch.items), n, _ptr(batch.reads), batch.reads.size, _ptr(batch.counts),
+            0 if batch.counts is None else batch.counts.size, _ptr(batch.haps), batch.haps.size, _ptr(batch.freqs),
+            0 if batch.freqs is None else batch.freqs.size, _ptr(alleles), batch.pmax, _ptr(stats), _ptr(freqs),
+            _ptr(occur), batch.hap_total, _ptr(results)))
+        return dict(alleles=alleles, stats=stats, freqs=freqs, occur=occur, results=results)
+
+    def genotype_likelihoods(self, batch):
+        """calling/exact.py:266-292 for a CallBatch -> float32 array (items back to back)."""
+        gl = np.zeros(max(batch.gl_total, 1), dtype=np.float32)
+        results = np.zeros(batch.n, dtype=ITEM_RESULT_DTYPE)
+        self._check(self._lib.mchb_genotype_likelihoods_batch(
+            self._h, L.MEM_HOST, _ptr(batch.items), batch.n, _ptr(batch.reads), batch.reads.size, _ptr(batch.counts),
+            0 if batch.counts is None else batch.counts.size, _ptr(batch.haps), batch.haps.size, _ptr(gl),
+            batch.gl_total, _ptr(results)))
+        return gl[: batch.gl_total]
+
+    def genotype_posteriors(self, items, llks, freqs, gl_total, hap_total, with_frequencies=False):
+        """calling/exact.py:295-329 (+ 332-369) from stored llk arrays (float32 or float64)."""
+        llks = np.ascontiguousarray(llks)
+        is32 = llks.dtype == np.float32
+        if not is32:
+            llks = np.ascontiguousarray(llks, dtype=np.float64)
+        gp = np.zeros(max(gl_total, 1), dtype=np.float64)
+        of = oc = oo = None
+        if with_frequencies:
+            of = np.zeros(max(hap_total, 1))
+            oc = np.zeros(max(hap_total, 1))
+            oo = np.zeros(max(hap_total, 1))
+        self._check(self._lib.mchb_genotype_posteriors_batch(
+            self._h, L.MEM_HOST, _ptr(items), len(items), _ptr(freqs), 0 if freqs is None else freqs.size, _ptr(llks),
+            1 if is32 else 0, gl_total, _ptr(gp), _ptr(of), _ptr(oc), _ptr(oo), hap_total))
+        return gp[:gl_total], of, oc, oo
+
     # ------------------------------------------------------------------ K2
     def assemble_call(self, items, params, reads, counts, n_alleles, initial, out_genotypes, out_llks,
                       lens, mem=L.MEM_HOST, keepalive=()):
@@ -172,6 +216,71 @@ class Device:
             _ptr(out_llks), int(lens[5]), _ptr(results))
         self._check(rc)
         return results
+
+
+def count_genotypes(n_haplotypes, ploidy):
+    """Number of multisets of size ploidy over n_haplotypes (combinatorics.py:35-54, exact integer)."""
+    from math import comb
+
+    return comb(int(n_haplotypes) + int(ploidy) - 1, int(ploidy))
+
+
+class CallBatch:
+    """Packed inputs of a batch of call / call-exact items (host arrays + descriptors)."""
+
+    def __init__(self, reads_list, haplotypes_list, ploidy, counts_list=None, priors=None):
+        n = len(reads_list)
+        self.n = n
+        items = np.zeros(n, dtype=CALL_ITEM_DTYPE)
+        ploidies = np.broadcast_to(np.asarray(ploidy, dtype=np.int64), (n,))
+        rs, hs, cs, fs = [], [], [], []
+        ro = ho = co = fo = oo = go = 0
+        use_counts = counts_list is not None and any(c is not None for c in counts_list)
+        self.n_genotypes = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
+            hp = np.ascontiguousarray(haplotypes_list[i], dtype=np.int8)
+            assert r.ndim == 3 and hp.ndim == 2 and hp.shape[1] == r.shape[1]
+            U, N, A = r.shape
+            H = hp.shape[0]
+            P = int(ploidies[i])
+            prior = None if priors is None else priors[i]
+            it = items[i]
+            it["reads_off"], it["counts_off"], it["haps_off"] = ro, co, ho
+            it["hap_out_off"], it["gl_off"] = oo, go
+            it["n_reads"], it["n_pos"], it["max_allele"], it["ploidy"], it["n_haps"] = U, N, A, P, H
+            it["freqs_off"] = -1
+            it["inbreeding"] = np.nan
+            if prior is not None:
+                inb, fr = prior
+                it["inbreeding"] = float(inb)
+                if fr is not None:
+                    fr = np.ascontiguousarray(fr, dtype=np.float64)
+                    assert len(fr) == H
+                    it["freqs_off"] = fo
+                    fs.append(fr)
+                    fo += H
+            G = count_genotypes(H, P)
+            self.n_genotypes[i] = G
+            rs.append(r.ravel())
+            hs.append(hp.ravel())
+            ro += r.size
+            ho += hp.size
+            oo += H
+            go += G
+            if use_counts:
+                c = counts_list[i]
+                c = np.ones(U, dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64)
+                cs.append(c)
+                co += U
+        self.items = items
+        self.reads = np.concatenate(rs) if rs else np.zeros(0)
+        self.haps = np.concatenate(hs) if hs else np.zeros(0, dtype=np.int8)
+        self.counts = np.concatenate(cs) if use_counts else None
+        self.freqs = np.concatenate(fs) if fs else None
+        self.hap_total = oo
+        self.gl_total = go
+        self.pmax = int(ploidies.max()) if n else 1
 
 
 def make_assemble_params(steps, chains, fix_homozygous, p_recombination, p_partial_dosage, p_dosage,

@@ -18,7 +18,10 @@
 //     are cached in shared memory; a proposal recomputes only the changed haplotype(s).  The
 //     evaluated value is a deterministic function of the ordered genotype (same instruction
 //     sequence whether cached or recomputed), as in the reference;
-//   * log-sum over reads = per-lane log() + xor-butterfly (uniform result in all lanes).
+//   * log-sum over reads = per-lane log() + xor-butterfly (uniform result in all lanes);
+//   * the steady-state loop is kept small enough for the instruction cache: one copy of each
+//     step function (structural sub-steps share one call site), rarely executed set-up code in
+//     separate non-inlined functions, the prior code compiled only into the PRIOR variant.
 #pragma once
 #include "common.cuh"
 
@@ -63,18 +66,19 @@ __device__ __forceinline__ uint64_t nib_set(uint64_t v, int i, int x) {
 }
 
 // increment a nibble-packed sorted genotype to its VCF-order successor (jitutils.py:113-146)
-__device__ __forceinline__ uint64_t increment_packed(uint64_t g, int P) {
+__device__ __noinline__ uint64_t increment_packed(uint64_t g, int P) {
     if (P == 1) return g + 1;
     int prev = nib(g, 0);
+#pragma unroll 1
     for (int i = 1; i < P; i++) {
         int al = nib(g, i);
         if (al == prev) continue;
         g = nib_set(g, i - 1, nib(g, i - 1) + 1);  // al > prev for sorted input
-        for (int m = 0; m < i - 1; m++) g = nib_set(g, m, 0);
+        g &= ~((1ull << (4 * (i - 1))) - 1ull);
         return g;
     }
     g = nib_set(g, P - 1, nib(g, P - 1) + 1);
-    for (int m = 0; m < P - 1; m++) g = nib_set(g, m, 0);
+    g &= ~((1ull << (4 * (P - 1))) - 1ull);
     return g;
 }
 
@@ -88,9 +92,11 @@ __device__ __noinline__ double snp_log_genotype_prior(uint64_t g, int P, int n_a
         alpha = (1.0 / (double)n_alleles) * ((1.0 - inbreeding) / inbreeding);
         lg_alpha = lgamma(alpha);
     }
+#pragma unroll 1
     for (int i = 0; i < P; i++) {
         int cntv = 0;
         bool first = true;
+#pragma unroll 1
         for (int k = 0; k < P; k++) {
             bool eq = nib(g, k) == nib(g, i);
             cntv += eq;
@@ -105,7 +111,106 @@ __device__ __noinline__ double snp_log_genotype_prior(uint64_t g, int P, int n_a
     return ((LGAMMA_INT[P + 1] + lgamma(sum_alphas)) - lgamma((double)P + sum_alphas)) + acc;
 }
 
-template <int CH>
+// ---------------------------------------------------------------------------------------
+// structural.py: options of a label matrix (lin = inside-interval labels, lout = outside labels,
+// nibble packed).  type 0: recombination (75-178), type 1: dosage swap (182-307).  Returns the
+// number of options; when o0 != nullptr the (h0, h1) pairs are written in the reference's order.
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ int structural_options(uint64_t lin, uint64_t lout, int P, int type, uint8_t *o0,
+                                               uint8_t *o1) {
+    // bit h of ff: row h is not a duplicate of an earlier row (haplotype_dosage != 0)
+    // bit h of sf: h is the first haplotype carrying its inside segment (segment_dosage != 0)
+    // bit h of ss: h is the only haplotype carrying its inside segment (segment_dosage == 1)
+    uint32_t ff = 0, sf = 0, ss = 0;
+#pragma unroll 1
+    for (int h = 0; h < P; h++) {
+        const int li = nib(lin, h), lo = nib(lout, h);
+        bool dup_full = false, dup_seg = false;
+        int c = 0;
+#pragma unroll 1
+        for (int k = 0; k < P; k++) {
+            const bool eq = nib(lin, k) == li;
+            c += eq;
+            dup_seg = dup_seg || (eq && k < h);
+            dup_full = dup_full || (eq && k < h && nib(lout, k) == lo);
+        }
+        ff |= (dup_full ? 0u : 1u) << h;
+        sf |= (dup_seg ? 0u : 1u) << h;
+        ss |= (c == 1 ? 1u : 0u) << h;
+    }
+    int n = 0;
+#pragma unroll 1
+    for (int h0 = 0; h0 < P; h0++) {
+        if (!((ff >> h0) & 1)) continue;               // duplicate copy of a haplotype
+        if (type == 1 && ((ss >> h0) & 1)) continue;   // would delete the only copy of the segment
+        const int li0 = nib(lin, h0), lo0 = nib(lout, h0);
+#pragma unroll 1
+        for (int h1 = (type == 0 ? h0 + 1 : 0); h1 < P; h1++) {
+            if (type == 0) {
+                if (!((ff >> h1) & 1)) continue;
+                if (nib(lin, h1) == li0 || nib(lout, h1) == lo0) continue;  // equivalent genotype
+            } else {
+                if (!((sf >> h1) & 1)) continue;   // donor segment already visited
+                if (nib(lin, h1) == li0) continue; // identical segment
+            }
+            if (o0) {
+                o0[n] = (uint8_t)h0;
+                o1[n] = (uint8_t)h1;
+            }
+            n++;
+        }
+    }
+    return n;
+}
+
+// structural.py:311-430 haplotype_segment_labels on packed keys: first-occurrence labels of the
+// inside-interval (.x) and outside-interval (.y) segments
+__device__ __noinline__ ulonglong2 segment_labels(const uint64_t *ks, int P, uint64_t mask_in) {
+    uint64_t li = 0, lo = 0;
+#pragma unroll 1
+    for (int h = 1; h < P; h++) {
+        const uint64_t kk = ks[h];
+        int fi = h, fo = h;
+#pragma unroll 1
+        for (int k = h - 1; k >= 0; k--) {
+            const uint64_t d = ks[k] ^ kk;
+            if ((d & mask_in) == 0) fi = k;
+            if ((d & ~mask_in) == 0) fo = k;
+        }
+        li |= (uint64_t)fi << (4 * h);
+        lo |= (uint64_t)fo << (4 * h);
+    }
+    return make_ulonglong2(li, lo);
+}
+
+// assemble/prior.py:15-112 from P comparable row identifiers (keys or label pairs) held in a
+// small uniform array; the first-occurrence dosage (jitutils.get_haplotype_dosage 377-422) is
+// evaluated on the fly and the terms are accumulated in row order like the reference.
+__device__ __noinline__ double assemble_prior_rows(const uint64_t *rows, int P, const double *scv,
+                                                   const double *lgd) {
+    const bool null_prior = scv[SC_INBREEDING] == 0.0;
+    const double lg_disp = scv[SC_LG_DISP];
+    double acc = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < P; i++) {
+        const uint64_t ki = rows[i];
+        int cntv = 0;
+        bool first = true;
+#pragma unroll 1
+        for (int k = 0; k < P; k++) {
+            bool eq = rows[k] == ki;
+            cntv += eq;
+            first = first && !(eq && k < i);
+        }
+        const int dose = first ? cntv : 0;
+        if (null_prior) acc += LGAMMA_INT[dose + 1];
+        else if (dose > 0) acc += lgd[dose] - (LGAMMA_INT[dose + 1] + lg_disp);
+    }
+    if (null_prior) return (LGAMMA_INT[P + 1] - acc) - (double)P * scv[SC_LUH];
+    return ((LGAMMA_INT[P + 1] + scv[SC_LG_SUMDISP]) - scv[SC_LG_P_SUMDISP]) + acc;
+}
+
+template <int CH, bool PRIOR>
 struct AsmCtx {
     static constexpr int UPAD = CH * 32;
     const AsmArgs &a;
@@ -113,7 +218,7 @@ struct AsmCtx {
     int lane;
     int N, A, P, B;
     uint32_t amask;
-    bool pow2, has_inb;
+    bool pow2;
     double invP;
     uint32_t slots;  // nibble t -> state slot (parallel tempering swaps exchange slots)
     WordStream ws;
@@ -129,7 +234,6 @@ struct AsmCtx {
     __device__ __forceinline__ double *oll() const { return reinterpret_cast<double *>(sm + a.o_oll); }
     __device__ __forceinline__ double *opr() const { return reinterpret_cast<double *>(sm + a.o_opr); }
     __device__ __forceinline__ double *lgdisp() const { return reinterpret_cast<double *>(sm + a.o_lgdisp); }
-    __device__ __forceinline__ double *homlp() const { return reinterpret_cast<double *>(sm + a.o_homlp); }
     __device__ __forceinline__ double *llk_t() const { return reinterpret_cast<double *>(sm + a.o_llk_t); }
     __device__ __forceinline__ double *sc() const { return reinterpret_cast<double *>(sm + a.o_sc); }
     __device__ __forceinline__ uint64_t *key() const { return reinterpret_cast<uint64_t *>(sm + a.o_key); }
@@ -141,6 +245,8 @@ struct AsmCtx {
     __device__ __forceinline__ uint8_t *opt1() const { return sm + a.o_opt1; }
     __device__ __forceinline__ uint8_t *ivb() const { return sm + a.o_ivb; }
     __device__ __forceinline__ uint8_t *ivp() const { return sm + a.o_ivp; }
+    // scratch rows for the prior (reuses the interval permutation area + padding: P u64 values)
+    __device__ __forceinline__ uint64_t *prow() const { return reinterpret_cast<uint64_t *>(sm + a.o_homlp); }
 
     __device__ __forceinline__ int slot(int t) const { return (int)((slots >> (4 * t)) & 15u); }
     __device__ __forceinline__ uint64_t *keys(int s) const { return key() + s * P; }
@@ -148,6 +254,7 @@ struct AsmCtx {
     // jitutils.random_choice (77-92): p (uniform, shared memory) is overwritten by its cumsum
     __device__ __forceinline__ int random_choice_inplace(double *p, int n) {
         double acc = 0.0;
+#pragma unroll 1
         for (int i = 0; i < n; i++) {
             acc += p[i];
             p[i] = acc;
@@ -163,6 +270,7 @@ struct AsmCtx {
         for (int ch = 0; ch < CH; ch++) out[ch] = 1.0;
         const double *base = Rt() + lane;
         const int stride = A * UPAD;
+#pragma unroll 2
         for (int j = 0; j < N; j++) {
             int al = (int)((uint32_t)k & amask);
             k >>= B;
@@ -191,6 +299,7 @@ struct AsmCtx {
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) {
             double rp = 0.0;
+#pragma unroll 2
             for (int h = 0; h < P; h++) {
                 double v = qq[h * UPAD + ch * 32];
                 v = (h == hA) ? qa[ch] : v;
@@ -214,6 +323,7 @@ struct AsmCtx {
     // (jitutils.count_haplotype_copies 349-374)
     __device__ __forceinline__ int count_copies(const uint64_t *ks, int hs, uint64_t kh) const {
         int c = 0;
+#pragma unroll 2
         for (int i = 0; i < P; i++) {
             uint64_t k = (i == hs) ? kh : ks[i];
             c += (k == kh);
@@ -221,45 +331,29 @@ struct AsmCtx {
         return c;
     }
 
-    // assemble/prior.py:15-112 from P comparable row identifiers sel(i); the first-occurrence
-    // dosage (jitutils.get_haplotype_dosage 377-422) is evaluated on the fly, terms are
-    // accumulated in row order like the reference
-    template <typename F>
-    __device__ __forceinline__ double prior_generic(F sel) const {
-        const double *scv = sc();
-        const bool null_prior = scv[SC_INBREEDING] == 0.0;
-        const double *lgd = lgdisp();
-        const double lg_disp = scv[SC_LG_DISP];
-        double acc = 0.0;
+    // prior of the haplotype keys of a slot with up to two haplotypes replaced
+    __device__ __forceinline__ double prior_of_keys(const uint64_t *ks, int hA, uint64_t kA, int hB, uint64_t kB) const {
+        uint64_t *rows = prow();
+        __syncwarp();
+#pragma unroll 1
         for (int i = 0; i < P; i++) {
-            const uint64_t ki = sel(i);
-            int cntv = 0;
-            bool first = true;
-            for (int k = 0; k < P; k++) {
-                bool eq = sel(k) == ki;
-                cntv += eq;
-                first = first && !(eq && k < i);
-            }
-            const int dose = first ? cntv : 0;
-            if (null_prior) acc += LGAMMA_INT[dose + 1];
-            else if (dose > 0) acc += lgd[dose] - (LGAMMA_INT[dose + 1] + lg_disp);
-        }
-        if (null_prior) return (LGAMMA_INT[P + 1] - acc) - (double)P * scv[SC_LUH];
-        return ((LGAMMA_INT[P + 1] + scv[SC_LG_SUMDISP]) - scv[SC_LG_P_SUMDISP]) + acc;
-    }
-
-    __device__ double prior_of_keys(const uint64_t *ks, int hA, uint64_t kA, int hB, uint64_t kB) const {
-        return prior_generic([=](int i) {
             uint64_t v = ks[i];
             v = (i == hA) ? kA : v;
             v = (i == hB) ? kB : v;
-            return v;
-        });
+            rows[i] = v;
+        }
+        __syncwarp();
+        return assemble_prior_rows(rows, P, sc(), lgdisp());
     }
 
     // prior of a label matrix (structural.py:546: dosage of the (inside, outside) label rows)
-    __device__ double prior_of_labels(uint64_t lin, uint64_t lout) const {
-        return prior_generic([=](int i) { return (uint64_t)((nib(lin, i) << 4) | nib(lout, i)); });
+    __device__ __forceinline__ double prior_of_labels(uint64_t lin, uint64_t lout) const {
+        uint64_t *rows = prow();
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < P; i++) rows[i] = (uint64_t)((nib(lin, i) << 4) | nib(lout, i));
+        __syncwarp();
+        return assemble_prior_rows(rows, P, sc(), lgdisp());
     }
 
     // ------------------------------------------------------------------ mutation.py:15-161
@@ -271,10 +365,37 @@ struct AsmCtx {
         const int cur = (int)((uint32_t)(kh >> shift) & amask);
         const double lhap = LOG_INT[count_copies(ks, -1, kh)];
         double lprior = 0.0;
-        if (has_inb) lprior = prior_of_keys(ks, -1, 0, -1, 0);
+        if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
+        double qn[CH];
+        if (n_all == 2 && cur < 2) {
+            // bi-allelic position: one proposal; identical arithmetic to the general path below
+            // (log(n_options) = log(1) = 0, exp(-inf) = 0 for the current allele)
+            const uint64_t kn = (kh & clr) | ((uint64_t)(cur ^ 1) << shift);
+            hap_products(kn, qn);
+            const double llk_o = eval_llk(s, h, qn, -1, qn);
+            double lprior_ratio = 0.0;
+            if (PRIOR) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - lprior;
+            const double lprop = LOG_INT[count_copies(ks, h, kn)] - lhap;
+            const double mh = ((llk_o - llk) + lprior_ratio) * temp + lprop;
+            const double p_o = exp(np_minimum0(mh) - 0.0);
+            const double p_c = 1 - p_o;  // 1 - (0 + p_o)
+            const double cs0 = cur == 0 ? p_c : p_o;
+            const double cs1 = cs0 + (cur == 0 ? p_o : p_c);
+            const double u = ws.next_double(lane);
+            const int choice = (cs1 <= u) ? 2 : ((cs0 <= u) ? 1 : 0);
+            if (choice >= 2) {
+                err = MCHB_ITEM_CHOICE_RANGE;
+                return;
+            }
+            if (choice != cur) {
+                commit(s, h, kn, qn);
+                llk = llk_o;
+            }
+            return;
+        }
         double *ol = oll(), *op = opr();
         int n_options = 0;
-        double qn[CH];
+#pragma unroll 1
         for (int i = 0; i < n_all; i++) {
             if (i == cur) {
                 ol[i] = llk;
@@ -287,16 +408,20 @@ struct AsmCtx {
                 ol[i] = llk_i;
                 const double llk_ratio = llk_i - llk;
                 double lprior_ratio = 0.0;
-                if (has_inb) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - lprior;
+                if (PRIOR) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - lprior;
                 const double lprop = LOG_INT[count_copies(ks, h, kn)] - lhap;
                 const double mh = (llk_ratio + lprior_ratio) * temp + lprop;
                 op[i] = np_minimum0(mh);
             }
         }
         const double ln_opts = LOG_INT[n_options];
-        for (int i = 0; i < n_all; i++) op[i] = exp(op[i] - ln_opts);
         double sum = 0.0;
-        for (int i = 0; i < n_all; i++) sum += op[i];
+#pragma unroll 1
+        for (int i = 0; i < n_all; i++) {
+            const double p = exp(op[i] - ln_opts);
+            op[i] = p;
+            sum += p;
+        }
         op[cur] = 1 - sum;
         const int choice = random_choice_inplace(op, n_all);
         if (choice >= n_all) {
@@ -321,6 +446,7 @@ struct AsmCtx {
             pm[i] = (uint16_t)((h << 8) | j);
         }
         __syncwarp();
+#pragma unroll 1
         for (int i = n - 1; i > 0; i--) {  // np.random.shuffle of the rows
             int k = ws.randint(i + 1, lane);
             uint16_t x = pm[i], y = pm[k];
@@ -330,6 +456,7 @@ struct AsmCtx {
         }
         __syncwarp();
         const uint8_t *na = nall();
+#pragma unroll 1
         for (int i = 0; i < n && !err; i++) {
             int hj = pm[i];
             int j = hj & 255;
@@ -337,137 +464,46 @@ struct AsmCtx {
         }
     }
 
-    // ------------------------------------------------------------------ structural.py:311-430
-    __device__ __forceinline__ void segment_labels(const uint64_t *ks, uint64_t mask_in, uint64_t &lin,
-                                                   uint64_t &lout) const {
-        lin = 0;
-        lout = 0;
-        for (int h = 1; h < P; h++) {
-            const uint64_t kk = ks[h];
-            int fi = h, fo = h;
-            for (int k = h - 1; k >= 0; k--) {
-                const uint64_t d = ks[k] ^ kk;
-                if ((d & mask_in) == 0) fi = k;
-                if ((d & ~mask_in) == 0) fo = k;
-            }
-            lin |= (uint64_t)fi << (4 * h);
-            lout |= (uint64_t)fo << (4 * h);
-        }
-    }
-
-    // bit h set when row h of the (lin, lout) label matrix is not a duplicate of an earlier row
-    __device__ __forceinline__ uint32_t first_full(uint64_t lin, uint64_t lout) const {
-        uint32_t m = 0;
-        for (int h = 0; h < P; h++) {
-            bool dup = false;
-            for (int k = 0; k < h; k++) dup = dup || (nib(lin, k) == nib(lin, h) && nib(lout, k) == nib(lout, h));
-            m |= (dup ? 0u : 1u) << h;
-        }
-        return m;
-    }
-
-    // bit h set when h is the first haplotype carrying its inside segment / the only one carrying it
-    __device__ __forceinline__ void segment_stats(uint64_t lin, uint32_t &seg_first, uint32_t &seg_single) const {
-        seg_first = 0;
-        seg_single = 0;
-        for (int h = 0; h < P; h++) {
-            bool dup = false;
-            int c = 0;
-            for (int k = 0; k < P; k++) {
-                bool eq = nib(lin, k) == nib(lin, h);
-                c += eq;
-                dup = dup || (eq && k < h);
-            }
-            seg_first |= (dup ? 0u : 1u) << h;
-            seg_single |= (c == 1 ? 1u : 0u) << h;
-        }
-    }
-
-    // structural.py:75-121 (count) / 124-178 (enumerate, WRITE)
-    template <bool WRITE>
-    __device__ __forceinline__ int recomb_options(uint64_t lin, uint64_t lout) const {
-        const uint32_t ff = first_full(lin, lout);
-        uint8_t *o0 = opt0(), *o1 = opt1();
-        int n = 0;
-        for (int h0 = 0; h0 < P; h0++) {
-            if (!((ff >> h0) & 1)) continue;
-            for (int h1 = h0 + 1; h1 < P; h1++) {
-                if (!((ff >> h1) & 1)) continue;
-                if (nib(lin, h0) == nib(lin, h1) || nib(lout, h0) == nib(lout, h1)) continue;
-                if (WRITE) {
-                    o0[n] = (uint8_t)h0;
-                    o1[n] = (uint8_t)h1;
-                }
-                n++;
-            }
-        }
-        return n;
-    }
-
-    // structural.py:182-236 (count) / 239-307 (enumerate, WRITE)
-    template <bool WRITE>
-    __device__ __forceinline__ int dosage_options(uint64_t lin, uint64_t lout) const {
-        const uint32_t ff = first_full(lin, lout);
-        uint32_t sf, ss;
-        segment_stats(lin, sf, ss);
-        uint8_t *o0 = opt0(), *o1 = opt1();
-        int n = 0;
-        for (int h0 = 0; h0 < P; h0++) {
-            if (!((ff >> h0) & 1)) continue;   // full duplicate of an earlier haplotype
-            if ((ss >> h0) & 1) continue;      // would delete the only copy of its segment
-            for (int h1 = 0; h1 < P; h1++) {
-                if (!((sf >> h1) & 1)) continue;  // donor segment already visited
-                if (nib(lin, h0) == nib(lin, h1)) continue;
-                if (WRITE) {
-                    o0[n] = (uint8_t)h0;
-                    o1[n] = (uint8_t)h1;
-                }
-                n++;
-            }
-        }
-        return n;
-    }
-
     // ------------------------------------------------------------------ structural.py:434-587
-    __device__ void interval_step(int s, int start, int stop, int step_type, double temp, double &llk) {
+    __device__ __forceinline__ void interval_step(int s, int start, int stop, int step_type, double temp,
+                                                  double &llk) {
         uint64_t *ks = keys(s);
         const int width = B * (stop - start);
         uint64_t mask_in = 0;
         if (width >= 64) mask_in = ~0ull;
         else if (width > 0) mask_in = ((1ull << width) - 1ull) << (B * start);
-        uint64_t lin, lout;
-        segment_labels(ks, mask_in, lin, lout);
+        const ulonglong2 labels = segment_labels(ks, P, mask_in);
+        const uint64_t lin = labels.x, lout = labels.y;
+        uint8_t *o0 = opt0(), *o1 = opt1();
         __syncwarp();
-        const int n_options = (step_type == 0) ? recomb_options<true>(lin, lout) : dosage_options<true>(lin, lout);
+        const int n_options = structural_options(lin, lout, P, step_type, o0, o1);
         __syncwarp();
         if (n_options == 0) return;  // no draw (structural.py:504-506)
         const double log_proposal = LOG_INV_INT[n_options];
         double lprior = 0.0;
-        if (has_inb) lprior = prior_of_keys(ks, -1, 0, -1, 0);
+        if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
         double *ol = oll(), *op = opr();
-        const uint8_t *o0 = opt0(), *o1 = opt1();
         double qa[CH], qb[CH];
+#pragma unroll 1
         for (int i = 0; i < n_options; i++) {
             const int h0 = o0[i], h1 = o1[i];
             const uint64_t k0 = ks[h0], k1 = ks[h1];
             const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
             uint64_t lin_o = nib_set(lin, h0, nib(lin, h1));
-            double llk_i;
+            int hB = -1;
             hap_products(k0n, qa);
             if (step_type == 0) {
                 const uint64_t k1n = (k0 & mask_in) | (k1 & ~mask_in);
                 lin_o = nib_set(lin_o, h1, nib(lin, h0));
                 hap_products(k1n, qb);
-                llk_i = eval_llk(s, h0, qa, h1, qb);
-            } else {
-                llk_i = eval_llk(s, h0, qa, -1, qa);
+                hB = h1;
             }
+            const double llk_i = eval_llk(s, h0, qa, hB, qb);
             ol[i] = llk_i;
             const double llk_ratio = llk_i - llk;
             double lprior_ratio = 0.0;
-            if (has_inb) lprior_ratio = prior_of_labels(lin_o, lout) - lprior;
-            const int n_return =
-                (step_type == 0) ? recomb_options<false>(lin_o, lout) : dosage_options<false>(lin_o, lout);
+            if (PRIOR) lprior_ratio = prior_of_labels(lin_o, lout) - lprior;
+            const int n_return = structural_options(lin_o, lout, P, step_type, nullptr, nullptr);
             const double lprop = LOG_INV_INT[n_return] - log_proposal;
             const double mh = (llk_ratio + lprior_ratio) * temp + lprop;
             op[i] = np_minimum0(mh);
@@ -475,9 +511,13 @@ struct AsmCtx {
         ol[n_options] = -INFINITY;
         op[n_options] = -INFINITY;
         const double ln_opts = LOG_INT[n_options];
-        for (int i = 0; i <= n_options; i++) op[i] = exp(op[i] - ln_opts);
         double sum = 0.0;
-        for (int i = 0; i <= n_options; i++) sum += op[i];
+#pragma unroll 1
+        for (int i = 0; i <= n_options; i++) {
+            const double p = exp(op[i] - ln_opts);
+            op[i] = p;
+            sum += p;
+        }
         op[n_options] = 1 - sum;
         const int choice = random_choice_inplace(op, n_options + 1);
         if (choice < n_options) {
@@ -495,55 +535,81 @@ struct AsmCtx {
         }
     }
 
-    // structural.py:23-71 random_breaks + 591-673 compound_step
-    __device__ void structural_step(int s, int n_breaks, int step_type, double temp, double &llk) {
-        if (n_breaks >= N) {
-            err = MCHB_ITEM_BREAKS;
-            return;
-        }
-        uint64_t avail = 0;  // candidate cut points 1..N-1
-        if (N >= 2) avail = ((N - 1 >= 64) ? ~0ull : ((1ull << (N - 1)) - 1ull)) << 1;
-        uint64_t cuts = 0;
-        for (int b = 0; b < n_breaks; b++) {
-            int m = __popcll(avail);
-            if (m == 0) break;
-            int k = ws.randint(m, lane);  // np.random.choice(options)
-            uint64_t t = avail;
-            for (int i = 0; i < k; i++) t &= t - 1;
-            int point = __ffsll((long long)t) - 1;
-            avail &= ~(1ull << point);
-            cuts |= 1ull << point;
-        }
+    // the three structural sub-steps of mcmc.py:347-394 share this single call site of
+    // interval_step: sub 0 = recombination over random intervals, sub 1 = dosage swap over
+    // random intervals (structural.py:23-71 random_breaks + 591-673 compound_step),
+    // sub 2 = dosage swap over the full length
+    __device__ __forceinline__ void structural_substeps(int s, double temp, double &llk, const double *brow, int blen) {
         uint8_t *vb = ivb(), *vp = ivp();
-        __syncwarp();
-        int nb = 0;
-        vb[nb++] = 0;
-        for (uint64_t t = cuts; t; t &= t - 1) vb[nb++] = (uint8_t)(__ffsll((long long)t) - 1);
-        vb[nb] = (uint8_t)N;
-        const int n_int = n_breaks + 1;
-        for (int i = 0; i < n_int; i++) vp[i] = (uint8_t)i;
-        __syncwarp();
-        for (int i = n_int - 1; i > 0; i--) {  // np.random.permutation(np.arange(n))
-            int k = ws.randint(i + 1, lane);
-            uint8_t x = vp[i], y = vp[k];
+#pragma unroll 1
+        for (int sub = 0; sub < 3 && !err; sub++) {
+            const double p_sub = sub == 0 ? a.p_recomb : (sub == 1 ? a.p_partial : a.p_dosage);
+            if (!(ws.next_double(lane) <= p_sub)) continue;
+            int n_int = 1;
             __syncwarp();
-            vp[i] = y;
-            vp[k] = x;
-        }
-        __syncwarp();
-        for (int i = 0; i < n_int && !err; i++) {
-            int p = vp[i];
-            interval_step(s, vb[p], vb[p + 1], step_type, temp, llk);
+            if (sub < 2) {
+                double *op = opr();
+#pragma unroll 1
+                for (int i = 0; i < blen; i++) op[i] = brow[i];
+                const int n_breaks = random_choice_inplace(op, blen);
+                if (n_breaks >= N) {
+                    err = MCHB_ITEM_BREAKS;
+                    return;
+                }
+                uint64_t avail = 0;  // candidate cut points 1..N-1
+                if (N >= 2) avail = ((N - 1 >= 64) ? ~0ull : ((1ull << (N - 1)) - 1ull)) << 1;
+                uint64_t cuts = 0;
+#pragma unroll 1
+                for (int b = 0; b < n_breaks; b++) {
+                    int m = __popcll(avail);
+                    if (m == 0) break;
+                    int k = ws.randint(m, lane);  // np.random.choice(options)
+                    uint64_t t = avail;
+#pragma unroll 1
+                    for (int i = 0; i < k; i++) t &= t - 1;
+                    int point = __ffsll((long long)t) - 1;
+                    avail &= ~(1ull << point);
+                    cuts |= 1ull << point;
+                }
+                int nb = 0;
+                vb[nb++] = 0;
+#pragma unroll 1
+                for (uint64_t t = cuts; t; t &= t - 1) vb[nb++] = (uint8_t)(__ffsll((long long)t) - 1);
+                vb[nb] = (uint8_t)N;
+                n_int = n_breaks + 1;
+#pragma unroll 1
+                for (int i = 0; i < n_int; i++) vp[i] = (uint8_t)i;
+                __syncwarp();
+#pragma unroll 1
+                for (int i = n_int - 1; i > 0; i--) {  // np.random.permutation(np.arange(n))
+                    int k = ws.randint(i + 1, lane);
+                    uint8_t x = vp[i], y = vp[k];
+                    __syncwarp();
+                    vp[i] = y;
+                    vp[k] = x;
+                }
+            } else {
+                vb[0] = 0;
+                vb[1] = (uint8_t)N;
+                vp[0] = 0;
+            }
+            __syncwarp();
+            const int step_type = sub == 0 ? 0 : 1;
+#pragma unroll 1
+            for (int i = 0; i < n_int && !err; i++) {
+                int p = vp[i];
+                interval_step(s, vb[p], vb[p + 1], step_type, temp, llk);
+            }
         }
     }
 
     // tempering.py:62-151 between temperature t (cooler, i) and t-1 (warmer, j)
-    __device__ void chain_swap_step(int t, double temp_i, double temp_j, double &llk_i) {
+    __device__ __forceinline__ void chain_swap_step(int t, double temp_i, double temp_j, double &llk_i) {
         const int si = slot(t), sj = slot(t - 1);
         double *lt = llk_t();
         double llk_j = lt[t - 1];
         double prior_i = 0.0, prior_j = 0.0;
-        if (has_inb) {
+        if (PRIOR) {
             prior_i = prior_of_keys(keys(si), -1, 0, -1, 0);
             prior_j = prior_of_keys(keys(sj), -1, 0, -1, 0);
         }
@@ -563,13 +629,205 @@ struct AsmCtx {
     }
 };
 
+// ---------------------------------------------------------------------------------------
+// Per-item set-up (runs once per item, kept out of line): stage the reads, homozygous fixing
+// (mcmc.py:495-541 + snpcalling.py:14-70), compaction of the variable positions, initial-state
+// distribution (mcmc.py:455-491, jitutils.py:483-487), gap -> 1.0, prior constants.
+// Returns n_het (>= 0) in the low 16 bits, bits per allele in bits 16..23.
+// ---------------------------------------------------------------------------------------
 template <int CH>
+__device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char *sm, int lane,
+                                                const mchb_assemble_item *itp, bool has_initial) {
+    constexpr int UPAD = CH * 32;
+    const int Nf = itp->n_pos, A = itp->max_allele, P = itp->ploidy;
+    const int Uin = itp->n_reads;
+    const int U = Uin > 0 ? Uin : 1;  // mcmc.py:132-137: one all-gap read stands in for none
+    const double inbreeding = itp->inbreeding;
+    const bool has_inb = !isnan(inbreeding);
+    const bool pow2 = (P & (P - 1)) == 0;
+    const double invP = 1.0 / (double)P;
+    double *Rt = reinterpret_cast<double *>(sm);
+    double *cnt = reinterpret_cast<double *>(sm + a.o_cnt);
+    double *homlp = reinterpret_cast<double *>(sm + a.o_homlp);
+    double *dist = reinterpret_cast<double *>(sm + a.o_dist);
+    double *opr = reinterpret_cast<double *>(sm + a.o_opr);
+    double *scv = reinterpret_cast<double *>(sm + a.o_sc);
+    double *lgd = reinterpret_cast<double *>(sm + a.o_lgdisp);
+    uint8_t *het = sm + a.o_het, *fixa = sm + a.o_fixa, *nall = sm + a.o_nall;
+    const int8_t *nal_full = a.n_alleles + itp->nalleles_off;
+
+    // ---- stage reads transposed: Rt[(j*A + al)*UPAD + r], raw values (NaN kept for now)
+    __syncwarp();
+    for (int i = lane; i < Nf * A * UPAD; i += 32) Rt[i] = 1.0;
+    for (int i = lane; i < UPAD; i += 32) cnt[i] = 0.0;
+    __syncwarp();
+    if (Uin > 0) {
+        const double *src = a.reads + itp->reads_off;
+        const int row = Nf * A;
+        const int tot = Uin * row;
+        for (int i = lane; i < tot; i += 32) {
+            int r = i / row;
+            int ja = i - r * row;
+            Rt[ja * UPAD + r] = __ldg(src + i);
+        }
+        for (int r = lane; r < Uin; r += 32) cnt[r] = a.counts ? (double)__ldg(a.counts + itp->counts_off + r) : 1.0;
+    } else {
+        for (int i = lane; i < Nf * A; i += 32) Rt[i * UPAD] = NAN;
+        if (lane == 0) cnt[0] = 1.0;
+    }
+    if (lane == 0) scv[SC_INBREEDING] = inbreeding;
+    __syncwarp();
+
+    // ---- homozygous fixing
+    int n_het = 0;
+#pragma unroll 1
+    for (int j = 0; j < Nf; j++) {
+        const int nA = nal_full[j];
+        const long long u_gens = comb_with_replacement(nA, P);
+        uint64_t g = 0;
+        double denom = 0.0;
+#pragma unroll 1
+        for (long long i = 0; i < u_gens; i++) {
+            double lprior = 0.0;
+            if (has_inb) lprior = snp_log_genotype_prior(g, P, nA, inbreeding);
+            double acc = 0.0;
+#pragma unroll
+            for (int ch = 0; ch < CH; ch++) {
+                double rp = 0.0;
+#pragma unroll 1
+                for (int h = 0; h < P; h++) {
+                    double v = Rt[(j * A + nib(g, h)) * UPAD + ch * 32 + lane];
+                    double prod = isnan(v) ? 1.0 : v;
+                    rp += pow2 ? prod * invP : prod / (double)P;
+                }
+                acc += log(rp) * cnt[ch * 32 + lane];
+            }
+            double lp = lprior + warp_sum(acc);
+            denom = (i == 0) ? lp : add_log_prob(denom, lp);
+            if (nib(g, 0) == nib(g, P - 1)) homlp[nib(g, 0)] = lp;
+            g = increment_packed(g, P);
+        }
+        __syncwarp();
+        int fixed = 0, fa = 0;
+#pragma unroll 1
+        for (int al = 0; al < nA; al++) {
+            double prob = exp(homlp[al] - denom);
+            if (prob >= a.fix_homozygous) {
+                fixed = 1;
+                fa = al;
+            }
+        }
+        __syncwarp();
+        fixa[j] = (uint8_t)fa;
+        if (!fixed) {
+            het[n_het] = (uint8_t)j;
+            nall[n_het] = (uint8_t)nA;
+            n_het++;
+        }
+    }
+    __syncwarp();
+    const int N = n_het;
+    if (N == 0) return 0;
+    int amax_het = 0;
+#pragma unroll 1
+    for (int k = 0; k < N; k++) amax_het = max(amax_het, (int)nall[k]);
+    if (has_initial) amax_het = max(amax_het, A);  // user states may use any allele < max_allele
+    int B = 1;
+    while ((1 << B) < amax_het) B++;
+
+    // ---- compact the variable positions (het[k] >= k, ascending: in-place is safe)
+#pragma unroll 1
+    for (int k = 0; k < N; k++) {
+        int j = het[k];
+        if (j != k)
+            for (int i = lane; i < A * UPAD; i += 32) Rt[k * A * UPAD + i] = Rt[j * A * UPAD + i];
+        __syncwarp();
+    }
+    // ---- initial-state distribution
+    if (!has_initial) {
+#pragma unroll 1
+        for (int k = 0; k < N; k++) {
+            int n_nonzero = 0;
+            uint32_t gapmask = 0;
+#pragma unroll 1
+            for (int al = 0; al < A; al++) {
+                const double *col = Rt + (k * A + al) * UPAD;
+                bool all_nan = true;
+#pragma unroll 1
+                for (int r = 0; r < U; r++) all_nan = all_nan && isnan(col[r]);
+                double tot = 0.0;
+                int cn = 0;
+                bool all_zero = true;
+#pragma unroll 1
+                for (int r = 0; r < U; r++) {
+                    double v = all_nan ? 1.0 : col[r];
+                    if (!isnan(v)) {
+                        tot += v;
+                        cn++;
+                    }
+                    if (!(v == 0.0)) all_zero = false;
+                }
+                __syncwarp();
+                dist[k * A + al] = tot / (double)cn;
+                if (all_nan) gapmask |= 1u << al;
+                if (!all_zero) n_nonzero++;
+            }
+            __syncwarp();
+            double s1 = 0.0;
+#pragma unroll 1
+            for (int al = 0; al < A; al++) {
+                double v = dist[k * A + al];
+                if ((gapmask >> al) & 1) v = 1.0 / (double)n_nonzero;
+                opr[al] = v;
+                s1 += v;
+            }
+            double s2 = 0.0;
+#pragma unroll 1
+            for (int al = 0; al < A; al++) {
+                double v = opr[al] / s1;
+                dist[k * A + al] = v;
+                s2 += v;
+            }
+#pragma unroll 1
+            for (int al = 0; al < A; al++) dist[k * A + al] = dist[k * A + al] / s2;
+            __syncwarp();
+        }
+    }
+    // ---- gaps become 1.0 from here on (likelihood.py:55-58)
+    for (int i = lane; i < N * A * UPAD; i += 32) {
+        double v = Rt[i];
+        if (isnan(v)) Rt[i] = 1.0;
+    }
+    __syncwarp();
+    // ---- per-item prior constants
+    {
+        float s = 0.0f;  // mcmc.py:294: float32 arithmetic in numba (int8 array)
+#pragma unroll 1
+        for (int k = 0; k < N; k++) s += LOGF_INT[nall[k]];
+        const double luh = (double)s;
+        __syncwarp();
+        scv[SC_LUH] = luh;
+        if (has_inb && inbreeding != 0.0) {
+            double log_disp = log((1.0 - inbreeding) / inbreeding) - luh;
+            double disp = exp(log_disp);
+            double sum_disp = exp(log_disp + luh);
+            scv[SC_LG_SUMDISP] = lgamma(sum_disp);
+            scv[SC_LG_P_SUMDISP] = lgamma((double)P + sum_disp);
+            scv[SC_LG_DISP] = lgamma(disp);
+#pragma unroll 1
+            for (int d = 1; d <= P; d++) lgd[d] = lgamma((double)d + disp);
+        }
+        __syncwarp();
+    }
+    return N | (B << 16);
+}
+
+template <int CH, bool PRIOR>
 __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ AsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int UPAD = CH * 32;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    AsmCtx<CH> c(a, smem_raw + (size_t)warp * a.smem_per_warp, lane);
+    AsmCtx<CH, PRIOR> c(a, smem_raw + (size_t)warp * a.smem_per_warp, lane);
 
     for (;;) {
         int w = 0;
@@ -579,9 +837,6 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
         const int item_id = a.order[w];
         const mchb_assemble_item *itp = a.items + item_id;
         const int Nf = itp->n_pos, A = itp->max_allele, P = itp->ploidy, T = itp->n_temps;
-        const int Uin = itp->n_reads;
-        const int U = Uin > 0 ? Uin : 1;  // mcmc.py:132-137: one all-gap read stands in for none
-        const double inbreeding = itp->inbreeding;
         const bool has_initial = a.initial != nullptr && itp->initial_off >= 0;
         c.A = A;
         c.P = P;
@@ -589,88 +844,16 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
         c.evals = 0;
         c.invP = 1.0 / (double)P;
         c.pow2 = (P & (P - 1)) == 0;
-        c.has_inb = !isnan(inbreeding);
         c.ws.init(a.words + (size_t)a.item_stream[item_id] * a.stream_len, a.stream_len, lane);
-        const int8_t *nal_full = a.n_alleles + itp->nalleles_off;
         int8_t *og = a.out_genotypes + itp->genotypes_off;
         double *ol = a.out_llks + itp->llks_off;
         const int step_sz = P * Nf;
-        double *Rt = c.Rt();
-        double *cnt = c.cnt();
 
-        // ---- stage reads transposed: Rt[(j*A + al)*UPAD + r], raw values (NaN kept for now)
-        __syncwarp();
-        for (int i = lane; i < Nf * A * UPAD; i += 32) Rt[i] = 1.0;
-        for (int i = lane; i < UPAD; i += 32) cnt[i] = 0.0;
-        __syncwarp();
-        if (Uin > 0) {
-            const double *src = a.reads + itp->reads_off;
-            const int row = Nf * A;
-            const int tot = Uin * row;
-            for (int i = lane; i < tot; i += 32) {
-                int r = i / row;
-                int ja = i - r * row;
-                Rt[ja * UPAD + r] = __ldg(src + i);
-            }
-            for (int r = lane; r < Uin; r += 32)
-                cnt[r] = a.counts ? (double)__ldg(a.counts + itp->counts_off + r) : 1.0;
-        } else {
-            for (int i = lane; i < Nf * A; i += 32) Rt[i * UPAD] = NAN;
-            if (lane == 0) cnt[0] = 1.0;
-        }
-        if (lane == 0) c.sc()[SC_INBREEDING] = inbreeding;
-        __syncwarp();
-
-        // ---- homozygous fixing: mcmc.py:495-541 + snpcalling.py:14-70
-        int n_het = 0;
-        {
-            double *homlp = c.homlp();
-            uint8_t *het = c.het(), *fixa = c.fixa(), *nall = c.nall();
-            for (int j = 0; j < Nf; j++) {
-                const int nA = nal_full[j];
-                const long long u_gens = comb_with_replacement(nA, P);
-                uint64_t g = 0;
-                double denom = 0.0;
-                for (long long i = 0; i < u_gens; i++) {
-                    double lprior = 0.0;
-                    if (c.has_inb) lprior = snp_log_genotype_prior(g, P, nA, inbreeding);
-                    double acc = 0.0;
-#pragma unroll
-                    for (int ch = 0; ch < CH; ch++) {
-                        double rp = 0.0;
-                        for (int h = 0; h < P; h++) {
-                            double v = Rt[(j * A + nib(g, h)) * UPAD + ch * 32 + lane];
-                            double prod = isnan(v) ? 1.0 : v;
-                            rp += c.pow2 ? prod * c.invP : prod / (double)P;
-                        }
-                        acc += log(rp) * cnt[ch * 32 + lane];
-                    }
-                    double lp = lprior + warp_sum(acc);
-                    denom = (i == 0) ? lp : add_log_prob(denom, lp);
-                    if (nib(g, 0) == nib(g, P - 1)) homlp[nib(g, 0)] = lp;
-                    g = increment_packed(g, P);
-                }
-                __syncwarp();
-                int fixed = 0, fa = 0;
-                for (int al = 0; al < nA; al++) {
-                    double prob = exp(homlp[al] - denom);
-                    if (prob >= a.fix_homozygous) {
-                        fixed = 1;
-                        fa = al;
-                    }
-                }
-                __syncwarp();
-                fixa[j] = (uint8_t)fa;
-                if (!fixed) {
-                    het[n_het] = (uint8_t)j;
-                    nall[n_het] = (uint8_t)nA;
-                    n_het++;
-                }
-            }
-        }
-        __syncwarp();
-        const int N = n_het;
+        const int setup = assemble_item_setup<CH>(a, c.sm, lane, itp, has_initial);
+        const int N = setup & 0xffff;
         c.N = N;
+        c.B = setup >> 16;
+        c.amask = (1u << c.B) - 1u;
 
         int status = 0;
         if (N == 0) {
@@ -682,118 +865,39 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
                 for (int i = lane; i < a.steps; i += 32) ol[(size_t)ch * a.steps + i] = NAN;
             }
         } else {
-            // bits per allele and shape limits
-            const uint8_t *nall = c.nall();
-            int amax_het = 0;
-            for (int k = 0; k < N; k++) amax_het = max(amax_het, (int)nall[k]);
-            if (has_initial) amax_het = max(amax_het, A);  // user states may use any allele < max_allele
-            int B = 1;
-            while ((1 << B) < amax_het) B++;
-            c.B = B;
-            c.amask = (1u << B) - 1u;
-            if (N * B > 64 || P > MCHB_MAX_PLOIDY || T > MCHB_MAX_TEMPS || T < 1) status = MCHB_ITEM_UNSUPPORTED;
+            if (N * c.B > 64 || P > MCHB_MAX_PLOIDY || T > MCHB_MAX_TEMPS || T < 1) status = MCHB_ITEM_UNSUPPORTED;
             if (!status && has_initial && itp->initial_nhet != N) status = MCHB_ITEM_INITIAL_SHAPE;
         }
         if (N > 0 && !status) {
-            const uint8_t *het = c.het(), *nall = c.nall();
+            const uint8_t *het = c.het();
             double *dist = c.dist(), *opr = c.opr();
-            // ---- compact the variable positions (het[k] >= k, ascending: in-place is safe)
-            for (int k = 0; k < N; k++) {
-                int j = het[k];
-                if (j != k)
-                    for (int i = lane; i < A * UPAD; i += 32) Rt[k * A * UPAD + i] = Rt[j * A * UPAD + i];
-                __syncwarp();
-            }
-            // ---- initial-state distribution: mcmc.py:455-491 then jitutils.py:483-487
-            if (!has_initial) {
-                for (int k = 0; k < N; k++) {
-                    int n_nonzero = 0;
-                    uint32_t gapmask = 0;
-                    for (int al = 0; al < A; al++) {
-                        const double *col = Rt + (k * A + al) * UPAD;
-                        bool all_nan = true;
-                        for (int r = 0; r < U; r++) all_nan = all_nan && isnan(col[r]);
-                        double tot = 0.0;
-                        int cn = 0;
-                        bool all_zero = true;
-                        for (int r = 0; r < U; r++) {
-                            double v = all_nan ? 1.0 : col[r];
-                            if (!isnan(v)) {
-                                tot += v;
-                                cn++;
-                            }
-                            if (!(v == 0.0)) all_zero = false;
-                        }
-                        __syncwarp();
-                        dist[k * A + al] = tot / (double)cn;
-                        if (all_nan) gapmask |= 1u << al;
-                        if (!all_zero) n_nonzero++;
-                    }
-                    __syncwarp();
-                    double s1 = 0.0;
-                    for (int al = 0; al < A; al++) {
-                        double v = dist[k * A + al];
-                        if ((gapmask >> al) & 1) v = 1.0 / (double)n_nonzero;
-                        opr[al] = v;
-                        s1 += v;
-                    }
-                    double s2 = 0.0;
-                    for (int al = 0; al < A; al++) {
-                        double v = opr[al] / s1;
-                        dist[k * A + al] = v;
-                        s2 += v;
-                    }
-                    for (int al = 0; al < A; al++) dist[k * A + al] = dist[k * A + al] / s2;
-                    __syncwarp();
-                }
-            }
-            // ---- gaps become 1.0 from here on (likelihood.py:55-58)
-            for (int i = lane; i < N * A * UPAD; i += 32) {
-                double v = Rt[i];
-                if (isnan(v)) Rt[i] = 1.0;
-            }
-            __syncwarp();
-            // ---- per-item prior constants
-            {
-                float s = 0.0f;  // mcmc.py:294: float32 arithmetic in numba (int8 array)
-                for (int k = 0; k < N; k++) s += LOGF_INT[nall[k]];
-                const double luh = (double)s;
-                double *scv = c.sc();
-                double *lgd = c.lgdisp();
-                __syncwarp();
-                scv[SC_LUH] = luh;
-                if (c.has_inb && inbreeding != 0.0) {
-                    double log_disp = log((1.0 - inbreeding) / inbreeding) - luh;
-                    double disp = exp(log_disp);
-                    double sum_disp = exp(log_disp + luh);
-                    scv[SC_LG_SUMDISP] = lgamma(sum_disp);
-                    scv[SC_LG_P_SUMDISP] = lgamma((double)P + sum_disp);
-                    scv[SC_LG_DISP] = lgamma(disp);
-                    for (int d = 1; d <= P; d++) lgd[d] = lgamma((double)d + disp);
-                }
-                __syncwarp();
-            }
             const int brow_i = min(N, a.break_rows - 1);
             const double *brow = a.break_table + (size_t)brow_i * a.break_stride;
             const int blen = a.break_len[brow_i];
             const double *temps = a.temperatures + itp->temps_off;
             double *lt = c.llk_t();
 
+#pragma unroll 1
             for (int chain = 0; chain < a.chains && !c.err; chain++) {
                 // ---- initial genotype written into state slot 0
                 uint64_t *k0 = c.keys(0);
                 __syncwarp();
                 if (has_initial) {
                     const int8_t *src = a.initial + itp->initial_off + (size_t)chain * P * N;
+#pragma unroll 1
                     for (int h = 0; h < P; h++) {
                         uint64_t k = 0;
+#pragma unroll 1
                         for (int j = 0; j < N; j++) k |= (uint64_t)((uint32_t)(uint8_t)src[h * N + j] & c.amask) << (c.B * j);
                         k0[h] = k;
                     }
                 } else {
+#pragma unroll 1
                     for (int h = 0; h < P; h++) {
                         uint64_t k = 0;
+#pragma unroll 1
                         for (int j = 0; j < N; j++) {
+#pragma unroll 1
                             for (int al = 0; al < A; al++) opr[al] = dist[j * A + al];
                             int choice = c.random_choice_inplace(opr, A);
                             if (choice >= A) c.err = MCHB_ITEM_CHOICE_RANGE;
@@ -808,21 +912,27 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
                 c.slots = 0x76543210u;
                 {
                     double qn[CH];
+#pragma unroll 1
                     for (int h = 0; h < P; h++) {
                         const uint64_t k = k0[h];
                         c.hap_products(k, qn);
+#pragma unroll 1
                         for (int t = 0; t < T; t++) c.commit(t, h, k, qn);
                     }
                     __syncwarp();
+                    // one base step on a non-existent haplotype index evaluates the current state
                     double llk0 = c.eval_llk(0, -1, qn, -1, qn);
                     c.evals--;  // the initial evaluation is not a proposal
+#pragma unroll 1
                     for (int t = 0; t < T; t++) lt[t] = llk0;
                     __syncwarp();
                 }
                 int8_t *ogc = og + (size_t)chain * a.steps * step_sz;
                 double *olc = ol + (size_t)chain * a.steps;
+#pragma unroll 1
                 for (int step = 0; step < a.steps && !c.err; step++) {
                     double llk = 0.0;
+#pragma unroll 1
                     for (int t = 0; t < T && !c.err; t++) {
                         llk = lt[t];
                         const int s = c.slot(t);
@@ -833,22 +943,8 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
                         }
                         c.mutation_compound_step(s, temp, llk);
                         if (c.err) break;
-                        if (c.ws.next_double(lane) <= a.p_recomb) {
-                            for (int i = 0; i < blen; i++) opr[i] = brow[i];
-                            int n_breaks = c.random_choice_inplace(opr, blen);
-                            c.structural_step(s, n_breaks, 0, temp, llk);
-                            if (c.err) break;
-                        }
-                        if (c.ws.next_double(lane) <= a.p_partial) {
-                            for (int i = 0; i < blen; i++) opr[i] = brow[i];
-                            int n_breaks = c.random_choice_inplace(opr, blen);
-                            c.structural_step(s, n_breaks, 1, temp, llk);
-                            if (c.err) break;
-                        }
-                        if (c.ws.next_double(lane) <= a.p_dosage) {
-                            c.interval_step(s, 0, N, 1, temp, llk);  // permutation of one interval draws nothing
-                            if (c.err) break;
-                        }
+                        c.structural_substeps(s, temp, llk, brow, blen);
+                        if (c.err) break;
                         if (t > 0) c.chain_swap_step(t, temp, temps[t - 1], llk);
                         __syncwarp();
                         lt[t] = llk;

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "aux_kernels.cuh"
 #include "assemble_kernel.cuh"
+#include "exact_kernel.cuh"
 
 using namespace mchb;
 
@@ -27,7 +28,8 @@ struct mchb_handle {
     int sm_count = 0;
     int smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream2 = nullptr;  // rare shape classes run beside the main launch
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     float kernel_ms = 0.f;
     int32_t launches = 0;
@@ -39,6 +41,7 @@ namespace {
 enum Slot {
     S_ITEMS = 0, S_ORDER, S_READS, S_COUNTS, S_NALLELES, S_INITIAL, S_OUT_G, S_OUT_L, S_RESULTS,
     S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
+    S_HAPS, S_FREQS, S_SCRATCH, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS,
     S_NSLOTS
 };
 
@@ -141,7 +144,10 @@ int mchb_create(int device, mchb_handle **out) {
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     h->bufs.resize(S_NSLOTS);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete h;
         return MCHB_ERR_CUDA;
     }
@@ -161,6 +167,9 @@ void mchb_destroy(mchb_handle *h) {
         if (b.p) cudaFree(b.p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -349,7 +358,7 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_oll = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_opr = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_lgdisp = take((size_t)(g.pmax + 2) * 8, 8);
-    args.o_homlp = take((size_t)g.amax * 8, 8);
+    args.o_homlp = take((size_t)std::max(g.amax, g.pmax) * 8, 8);  // also the prior's row scratch
     args.o_llk_t = take((size_t)g.tmax * 8, 8);
     args.o_key = take((size_t)g.tmax * g.pmax * 8, 8);
     args.o_sc = take((size_t)SC_COUNT * 8, 8);
@@ -364,8 +373,8 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     return (off + 15) & ~(size_t)15;
 }
 
-template <int CH>
-int launch_assemble(mchb_handle *h, AsmArgs &args, const AsmGeom &g, int n_items_class) {
+template <int CH, bool PRIOR>
+int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const AsmGeom &g, int n_items_class) {
     const size_t per_warp = asm_layout(g, CH, args);
     int warps_per_cta = 4;
     while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
@@ -374,9 +383,9 @@ int launch_assemble(mchb_handle *h, AsmArgs &args, const AsmGeom &g, int n_items
         return MCHB_ERR_ARGUMENT;
     }
     const size_t smem = per_warp * warps_per_cta;
-    CK(cudaFuncSetAttribute(assemble_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(assemble_kernel<CH, PRIOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, assemble_kernel<CH>, warps_per_cta * 32, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, assemble_kernel<CH, PRIOR>, warps_per_cta * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     long long want = ((long long)n_items_class + warps_per_cta - 1) / warps_per_cta;
     long long grid = std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
@@ -387,7 +396,7 @@ int launch_assemble(mchb_handle *h, AsmArgs &args, const AsmGeom &g, int n_items
     args.tmax = g.tmax;
     args.maxopt = g.maxopt;
     args.smem_per_warp = (int)per_warp;
-    assemble_kernel<CH><<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(args);
+    assemble_kernel<CH, PRIOR><<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(args);
     CK(cudaGetLastError());
     h->launches++;
     return MCHB_OK;
@@ -416,9 +425,10 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         h->err = "bad assemble parameters";
         return MCHB_ERR_ARGUMENT;
     }
-    // ---- validate, classify by unique-read chunk count, collect seeds
-    std::vector<int32_t> order[4];  // CH = 1, 2, 4, 8
-    AsmGeom geom[4];
+    constexpr int NCLS = 8;
+    // ---- validate, classify by unique-read chunk count and prior use, collect seeds
+    std::vector<int32_t> order[NCLS];  // class = 2 * log2(CH) + has_prior, CH = 1, 2, 4, 8
+    AsmGeom geom[NCLS];
     std::map<uint32_t, int32_t> seed_index;
     std::vector<uint32_t> seeds;
     std::vector<int32_t> item_stream((size_t)n_items, 0);
@@ -452,7 +462,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         if (it.n_pos == 0) {  // nothing to sample: empty traces, NaN llks are written by the host shim
             continue;
         }
-        int cls = it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 128 ? 2 : 3;
+        int cls = 2 * (it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 128 ? 2 : 3) + (std::isnan(it.inbreeding) ? 0 : 1);
         order[cls].push_back((int32_t)i);
         AsmGeom &g = geom[cls];
         g.nmax = std::max(g.nmax, it.n_pos);
@@ -471,7 +481,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         const int64_t per_step = (4 * pn + 10 * (int64_t)it.n_pos + 24) * it.n_temps;
         words_needed = std::max(words_needed, (int64_t)pp.chains * (2 * pn + 8 + (int64_t)pp.steps * per_step) + 64);
     }
-    for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < NCLS; c++) {
         AsmGeom &g = geom[c];
         g.maxopt = std::max({g.pmax * (g.pmax - 1), g.amax, (int)pp.break_stride, 2});
     }
@@ -510,11 +520,11 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     int64_t stream_len = pp.rng_words_hint > 0 ? pp.rng_words_hint : words_needed;
     if (pp.replay_words) stream_len = pp.replay_len;
     stream_len = (stream_len + 31) & ~(int64_t)31;
-    std::vector<int32_t> todo[4];
-    for (int c = 0; c < 4; c++) todo[c] = order[c];
+    std::vector<int32_t> todo[NCLS];
+    for (int c = 0; c < NCLS; c++) todo[c] = order[c];
     for (int attempt = 0; attempt < 6; attempt++) {
         int64_t total = 0;
-        for (int c = 0; c < 4; c++) total += (int64_t)todo[c].size();
+        for (int c = 0; c < NCLS; c++) total += (int64_t)todo[c].size();
         if (total == 0) break;
         uint32_t *dwords = nullptr;
         if (pp.replay_words) {
@@ -530,47 +540,76 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         void *dorder;
         if ((rc = ensure(h, S_ORDER, sizeof(int32_t) * (size_t)total, &dorder))) return rc;
         CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
-        CK(cudaEventRecord(h->ev0, h->stream));
-        int64_t off = 0;
-        for (int c = 0; c < 4; c++) {
-            if (todo[c].empty()) continue;
-            int32_t *dord = (int32_t *)dorder + off;
-            CK(cudaMemcpyAsync(dord, todo[c].data(), sizeof(int32_t) * todo[c].size(), cudaMemcpyHostToDevice, h->stream));
-            AsmArgs args;
-            memset(&args, 0, sizeof(args));
-            args.items = (const mchb_assemble_item *)ditems;
-            args.order = dord;
-            args.n_order = (int32_t)todo[c].size();
-            args.reads = dreads;
-            args.counts = dcounts;
-            args.n_alleles = dnall;
-            args.initial = dinit;
-            args.out_genotypes = dog;
-            args.out_llks = dol;
-            args.results = (mchb_item_result *)dresults;
-            args.words = dwords;
-            args.item_stream = (const int32_t *)dstream;
-            args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
-            args.steps = pp.steps;
-            args.chains = pp.chains;
-            args.fix_homozygous = pp.fix_homozygous;
-            args.p_recomb = pp.p_recombination;
-            args.p_partial = pp.p_partial_dosage;
-            args.p_dosage = pp.p_dosage;
-            args.break_table = (const double *)dbreaks;
-            args.break_len = (const int32_t *)dbreaklen;
-            args.break_rows = pp.break_rows;
-            args.break_stride = pp.break_stride;
-            args.temperatures = (const double *)dtemps;
-            args.work_counter = (int32_t *)dcounter + c;
-            switch (c) {
-                case 0: rc = launch_assemble<1>(h, args, geom[c], (int)todo[c].size()); break;
-                case 1: rc = launch_assemble<2>(h, args, geom[c], (int)todo[c].size()); break;
-                case 2: rc = launch_assemble<4>(h, args, geom[c], (int)todo[c].size()); break;
-                default: rc = launch_assemble<8>(h, args, geom[c], (int)todo[c].size()); break;
+        // the most populated class runs on the main stream; the rare classes are forked onto the
+        // second stream first so that their few long-running warps overlap the main launch
+        int main_cls = 0;
+        for (int c = 1; c < NCLS; c++)
+            if (todo[c].size() > todo[main_cls].size()) main_cls = c;
+        int64_t offs[NCLS];
+        {
+            int64_t off = 0;
+            for (int c = 0; c < NCLS; c++) {
+                offs[c] = off;
+                if (todo[c].empty()) continue;
+                CK(cudaMemcpyAsync((int32_t *)dorder + off, todo[c].data(), sizeof(int32_t) * todo[c].size(),
+                                   cudaMemcpyHostToDevice, h->stream));
+                off += (int64_t)todo[c].size();
             }
-            if (rc) return rc;
-            off += (int64_t)todo[c].size();
+        }
+        CK(cudaEventRecord(h->ev0, h->stream));
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        bool forked = false;
+        for (int pass = 0; pass < 2; pass++) {
+            for (int c = NCLS - 1; c >= 0; c--) {
+                if (todo[c].empty()) continue;
+                if ((pass == 0) == (c == main_cls)) continue;  // pass 0: rare classes, pass 1: main class
+                cudaStream_t st = (c == main_cls) ? h->stream : h->stream2;
+                if (c != main_cls) forked = true;
+                AsmArgs args;
+                memset(&args, 0, sizeof(args));
+                args.items = (const mchb_assemble_item *)ditems;
+                args.order = (int32_t *)dorder + offs[c];
+                args.n_order = (int32_t)todo[c].size();
+                args.reads = dreads;
+                args.counts = dcounts;
+                args.n_alleles = dnall;
+                args.initial = dinit;
+                args.out_genotypes = dog;
+                args.out_llks = dol;
+                args.results = (mchb_item_result *)dresults;
+                args.words = dwords;
+                args.item_stream = (const int32_t *)dstream;
+                args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
+                args.steps = pp.steps;
+                args.chains = pp.chains;
+                args.fix_homozygous = pp.fix_homozygous;
+                args.p_recomb = pp.p_recombination;
+                args.p_partial = pp.p_partial_dosage;
+                args.p_dosage = pp.p_dosage;
+                args.break_table = (const double *)dbreaks;
+                args.break_len = (const int32_t *)dbreaklen;
+                args.break_rows = pp.break_rows;
+                args.break_stride = pp.break_stride;
+                args.temperatures = (const double *)dtemps;
+                args.work_counter = (int32_t *)dcounter + c;
+                const int n_c = (int)todo[c].size();
+                switch (c) {
+                    case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c); break;
+                    case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c); break;
+                    case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c); break;
+                    case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c); break;
+                    case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c); break;
+                    case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c); break;
+                    case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c); break;
+                    default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c); break;
+                }
+                if (rc) return rc;
+            }
+        }
+        if (forked) {
+            CK(cudaEventRecord(h->ev_join, h->stream2));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         }
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
@@ -581,7 +620,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         if (pp.replay_words) break;
         // collect the items that ran out of words
         bool again = false;
-        for (int c = 0; c < 4; c++) {
+        for (int c = 0; c < NCLS; c++) {
             std::vector<int32_t> next;
             for (int32_t id : todo[c])
                 if (results[id].status == MCHB_ITEM_RNG_EXHAUSTED) next.push_back(id);
@@ -596,6 +635,248 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         CK(cudaMemcpyAsync(out_llks, dol, sizeof(double) * (size_t)out_llks_len, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    return MCHB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------ K4 call-exact
+namespace {
+
+struct CallGeom {
+    int umax = 1, hmax = 1, pmax = 1;
+    long long gmax = 1;
+};
+
+// validates the descriptors; G per item must fit the per-genotype arrays when use_gl
+int check_call_items(mchb_handle *h, const mchb_call_item *items, int64_t n_items, int64_t reads_len,
+                     bool has_counts, int64_t counts_len, int64_t haps_len, bool has_freqs, int64_t freqs_len,
+                     int64_t hap_out_len, int64_t gl_len, bool use_reads, CallGeom &g) {
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_call_item &it = items[i];
+        bool bad = it.n_reads < 0 || it.n_pos < 0 || it.max_allele < 0 || it.ploidy < 1 || it.n_haps < 1 ||
+                   it.ploidy > MCHB_MAX_PLOIDY || it.n_haps > 256;
+        if (!bad && use_reads) {
+            const int64_t rsz = (int64_t)it.n_reads * it.n_pos * it.max_allele;
+            bad = it.reads_off < 0 || it.reads_off + rsz > reads_len || it.haps_off < 0 ||
+                  it.haps_off + (int64_t)it.n_haps * it.n_pos > haps_len ||
+                  (has_counts && (it.counts_off < 0 || it.counts_off + it.n_reads > counts_len));
+        }
+        if (!bad && has_freqs && it.freqs_off >= 0) bad = it.freqs_off + it.n_haps > freqs_len;
+        if (!bad && hap_out_len >= 0) bad = it.hap_out_off < 0 || it.hap_out_off + it.n_haps > hap_out_len;
+        long long G = 0;
+        if (!bad) {
+            // C(H+P-1, P) with overflow guard (long double estimate first)
+            long double est = 1.0L;
+            for (int k = 1; k <= it.ploidy; k++) est = est * (long double)(it.n_haps + it.ploidy - k) / (long double)k;
+            if (est > 4.0e18L) bad = true;
+            else G = comb_exact((long long)it.n_haps + it.ploidy - 1, it.ploidy);
+        }
+        if (!bad && gl_len >= 0) bad = it.gl_off < 0 || it.gl_off + G > gl_len;
+        if (bad) {
+            h->err = "call item " + std::to_string(i) + " is inconsistent with the given array lengths or limits";
+            return MCHB_ERR_ARGUMENT;
+        }
+        g.umax = std::max(g.umax, it.n_reads);
+        g.hmax = std::max(g.hmax, it.n_haps);
+        g.pmax = std::max(g.pmax, it.ploidy);
+        g.gmax = std::max(g.gmax, G);
+    }
+    return MCHB_OK;
+}
+
+size_t exact_smem(const CallGeom &g) {
+    size_t d = (size_t)g.umax * g.hmax + g.umax + g.hmax + (size_t)g.hmax * (g.pmax + 1) + 2 * (size_t)g.hmax + 8;
+    return d * 8 + 4 * sizeof(ModeRec) + 64;
+}
+
+int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, int64_t n_items, const double *reads,
+              int64_t reads_len, const int64_t *counts, int64_t counts_len, const int8_t *haplotypes,
+              int64_t haplotypes_len, const double *freqs, int64_t freqs_len, int64_t *out_alleles, int32_t pstride,
+              double *out_stats, double *out_freqs, double *out_occur, int64_t hap_out_len, float *out_gl,
+              int64_t gl_len, mchb_item_result *results) {
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    if (n_items > 0x7fffffff) {
+        h->err = "too many items in one call";
+        return MCHB_ERR_ARGUMENT;
+    }
+    CallGeom g;
+    int rc = check_call_items(h, items, n_items, reads_len, counts != nullptr, counts_len, haplotypes_len,
+                              freqs != nullptr, freqs_len, mode == 0 ? hap_out_len : -1, mode == 1 ? gl_len : -1, true,
+                              g);
+    if (rc) return rc;
+    if (mode == 0 && pstride < g.pmax) {
+        h->err = "pstride smaller than the largest ploidy";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const size_t smem = exact_smem(g);
+    if (smem > (size_t)h->smem_optin) {
+        h->err = "call-exact item needs more shared memory than one CTA can have";
+        return MCHB_ERR_ARGUMENT;
+    }
+    void *ditems, *dcounter, *dresults;
+    if ((rc = ensure(h, S_ITEMS, sizeof(mchb_call_item) * (size_t)n_items, &ditems))) return rc;
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8, &dcounter))) return rc;
+    if ((rc = ensure(h, S_RESULTS, sizeof(mchb_item_result) * (size_t)n_items, &dresults))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_call_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+    const double *dreads, *dfreqs;
+    const int64_t *dcounts;
+    const int8_t *dhaps;
+    if ((rc = stage_in(h, mem, S_READS, reads, reads_len, &dreads))) return rc;
+    if ((rc = stage_in(h, mem, S_COUNTS, counts, counts_len, &dcounts))) return rc;
+    if ((rc = stage_in(h, mem, S_HAPS, haplotypes, haplotypes_len, &dhaps))) return rc;
+    if ((rc = stage_in(h, mem, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
+    CK(cudaFuncSetAttribute(exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exact_kernel, 128, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long grid = std::min<long long>(n_items, (long long)h->sm_count * ctas_per_sm);
+    ExactArgs a;
+    memset(&a, 0, sizeof(a));
+    a.items = (const mchb_call_item *)ditems;
+    a.n_items = (int32_t)n_items;
+    a.reads = dreads;
+    a.counts = dcounts;
+    a.haplotypes = dhaps;
+    a.freqs = dfreqs;
+    a.mode = mode;
+    a.work_counter = (int32_t *)dcounter;
+    a.results = (mchb_item_result *)dresults;
+    a.umax = g.umax;
+    a.hmax = g.hmax;
+    a.pmax = g.pmax;
+    a.pstride = pstride;
+    int64_t *dalleles = nullptr;
+    double *dstats = nullptr, *dfo = nullptr, *doc = nullptr;
+    float *dgl = nullptr;
+    if (mode == 0) {
+        void *scratch;
+        if ((rc = ensure(h, S_SCRATCH, sizeof(double) * (size_t)grid * (size_t)g.gmax, &scratch))) return rc;
+        a.scratch = (double *)scratch;
+        a.scratch_stride = g.gmax;
+        if ((rc = stage_out(h, mem, S_OUT_A, out_alleles, n_items * pstride, &dalleles))) return rc;
+        if ((rc = stage_out(h, mem, S_OUT_S, out_stats, n_items * 4, &dstats))) return rc;
+        if ((rc = stage_out(h, mem, S_OUT_F, out_freqs, hap_out_len, &dfo))) return rc;
+        if ((rc = stage_out(h, mem, S_OUT_O, out_occur, hap_out_len, &doc))) return rc;
+        a.out_alleles = dalleles;
+        a.out_stats = dstats;
+        a.out_freqs = dfo;
+        a.out_occur = doc;
+    } else {
+        if ((rc = stage_out(h, mem, S_OUT_GL, out_gl, gl_len, &dgl))) return rc;
+        a.out_gl = dgl;
+    }
+    CK(cudaEventRecord(h->ev0, h->stream));
+    exact_kernel<<<(unsigned)grid, 128, smem, h->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    if (results)
+        CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+    if (mem == MCHB_MEM_HOST) {
+        if (mode == 0) {
+            CK(cudaMemcpyAsync(out_alleles, dalleles, sizeof(int64_t) * (size_t)n_items * pstride, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(out_stats, dstats, sizeof(double) * (size_t)n_items * 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(out_freqs, dfo, sizeof(double) * (size_t)hap_out_len, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(out_occur, doc, sizeof(double) * (size_t)hap_out_len, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            CK(cudaMemcpyAsync(out_gl, dgl, sizeof(float) * (size_t)gl_len, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->kernel_ms, h->ev0, h->ev1));
+    return MCHB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mchb_call_exact_mode_batch(mchb_handle *h, int mem, const mchb_call_item *items, int64_t n_items,
+                               const double *reads, int64_t reads_len, const int64_t *counts, int64_t counts_len,
+                               const int8_t *haplotypes, int64_t haplotypes_len, const double *freqs,
+                               int64_t freqs_len, int64_t *out_alleles, int32_t pstride, double *out_stats,
+                               double *out_freqs, double *out_occur, int64_t hap_out_len, mchb_item_result *results) {
+    if (!h || !items || n_items < 0 || !out_alleles || !out_stats || !out_freqs || !out_occur) return MCHB_ERR_ARGUMENT;
+    return run_exact(h, mem, 0, items, n_items, reads, reads_len, counts, counts_len, haplotypes, haplotypes_len, freqs,
+                     freqs_len, out_alleles, pstride, out_stats, out_freqs, out_occur, hap_out_len, nullptr, 0, results);
+}
+
+int mchb_genotype_likelihoods_batch(mchb_handle *h, int mem, const mchb_call_item *items, int64_t n_items,
+                                    const double *reads, int64_t reads_len, const int64_t *counts, int64_t counts_len,
+                                    const int8_t *haplotypes, int64_t haplotypes_len, float *out_gl, int64_t gl_len,
+                                    mchb_item_result *results) {
+    if (!h || !items || n_items < 0 || !out_gl) return MCHB_ERR_ARGUMENT;
+    return run_exact(h, mem, 1, items, n_items, reads, reads_len, counts, counts_len, haplotypes, haplotypes_len, nullptr, 0,
+                     nullptr, 0, nullptr, nullptr, nullptr, 0, out_gl, gl_len, results);
+}
+
+int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item *items, int64_t n_items,
+                                   const double *freqs, int64_t freqs_len, const void *llks, int llk_is_f32,
+                                   int64_t gl_len, double *out_gp, double *out_freqs, double *out_counts,
+                                   double *out_occur, int64_t hap_out_len) {
+    if (!h || !items || n_items < 0 || !llks || !out_gp) return MCHB_ERR_ARGUMENT;
+    if (out_freqs && (!out_counts || !out_occur)) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    CallGeom g;
+    int rc = check_call_items(h, items, n_items, 0, false, 0, 0, freqs != nullptr, freqs_len, out_freqs ? hap_out_len : -1,
+                              gl_len, false, g);
+    if (rc) return rc;
+    const size_t smem = ((size_t)g.hmax * (g.pmax + 4) + 16) * 8;
+    void *ditems;
+    if ((rc = ensure(h, S_ITEMS, sizeof(mchb_call_item) * (size_t)n_items, &ditems))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_call_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    const double *dfreqs;
+    if ((rc = stage_in(h, mem, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
+    PosteriorArgs a;
+    memset(&a, 0, sizeof(a));
+    a.items = (const mchb_call_item *)ditems;
+    a.n_items = (int32_t)n_items;
+    a.freqs = dfreqs;
+    a.hmax = g.hmax;
+    a.pmax = g.pmax;
+    if (llk_is_f32) {
+        const float *d;
+        if ((rc = stage_in(h, mem, S_LLKS, (const float *)llks, gl_len, &d))) return rc;
+        a.llk32 = d;
+    } else {
+        const double *d;
+        if ((rc = stage_in(h, mem, S_LLKS, (const double *)llks, gl_len, &d))) return rc;
+        a.llk64 = d;
+    }
+    double *dgp, *dfo = nullptr, *dco = nullptr, *doc = nullptr;
+    if ((rc = stage_out(h, mem, S_OUT_GP, out_gp, gl_len, &dgp))) return rc;
+    a.out_gp = dgp;
+    if (out_freqs) {
+        if ((rc = stage_out(h, mem, S_OUT_F, out_freqs, hap_out_len, &dfo))) return rc;
+        if ((rc = stage_out(h, mem, S_OUT_C, out_counts, hap_out_len, &dco))) return rc;
+        if ((rc = stage_out(h, mem, S_OUT_O, out_occur, hap_out_len, &doc))) return rc;
+        a.out_freqs = dfo;
+        a.out_counts = dco;
+        a.out_occur = doc;
+    }
+    CK(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = std::min<long long>(n_items, (long long)h->sm_count * 8);
+    CK(cudaEventRecord(h->ev0, h->stream));
+    posterior_kernel<<<(unsigned)grid, 128, smem, h->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    if (mem == MCHB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_gp, dgp, sizeof(double) * (size_t)gl_len, cudaMemcpyDeviceToHost, h->stream));
+        if (out_freqs) {
+            CK(cudaMemcpyAsync(out_freqs, dfo, sizeof(double) * (size_t)hap_out_len, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(out_counts, dco, sizeof(double) * (size_t)hap_out_len, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(out_occur, doc, sizeof(double) * (size_t)hap_out_len, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->kernel_ms, h->ev0, h->ev1));
     return MCHB_OK;
 }
 
