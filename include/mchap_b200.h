@@ -212,6 +212,31 @@ int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item
                                    double *out_freqs, double *out_counts, double *out_occur,
                                    int64_t hap_out_len);
 
+/* ---- genotype calling MCMC over known haplotypes (mchap call) -----------------------------
+ * Replaces: calling/classes.py:49-124 CallingMCMC.fit (greedy_caller 393-453 for the initial
+ * genotype, mcmc_sampler 330-390, compound_step 232-327, gibbs_options 143-229 / mh_options
+ * 15-140).  Items are mchb_call_item records with two fields re-used: `reserved` = RNG seed
+ * (uint32), gl_off = element offset of the item's int32[chains, steps, P] trace in out_alleles,
+ * hap_out_off = element offset of its f64[chains, steps] llks in out_llks.
+ * initial: int32[n_items, pstride] or NULL; a row whose first entry is negative asks for the
+ * reference's greedy initialisation. */
+typedef struct {
+    int32_t steps, chains;
+    int32_t step_type;           /* 0 = Gibbs, 1 = Metropolis-Hastings */
+    int32_t reserved;
+    const uint32_t *replay_words; /* replay harness (HOST memory) or NULL */
+    int64_t replay_len;
+    int64_t rng_words_hint;
+} mchb_call_mcmc_params;
+
+int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcmc_params *params,
+                         const mchb_call_item *items, int64_t n_items, const double *reads,
+                         int64_t reads_len, const int64_t *counts, int64_t counts_len,
+                         const int8_t *haplotypes, int64_t haplotypes_len, const double *freqs,
+                         int64_t freqs_len, const int32_t *initial, int32_t pstride,
+                         int32_t *out_alleles, int64_t out_alleles_len, double *out_llks,
+                         int64_t out_llks_len, mchb_item_result *results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,8 +6,9 @@ library ``mchap_b200/_lib/libmchap_b200.so`` (C ABI in ``include/mchap_b200.h``)
 the library or an sm_100 device is missing — there is no CPU fallback.
 """
 from .assemble.mcmc import DenovoMCMC
+from .calling.classes import CallingMCMC
 from .api import Device, default_device, MchapB200Error
 
 __version__ = "0.1.0"
 
-__all__ = ["DenovoMCMC", "Device", "default_device", "MchapB200Error", "__version__"]
+__all__ = ["DenovoMCMC", "CallingMCMC", "Device", "default_device", "MchapB200Error", "__version__"]

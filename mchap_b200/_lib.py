@@ -95,6 +95,18 @@ class CallItem(C.Structure):
     ]
 
 
+class CallMcmcParams(C.Structure):
+    _fields_ = [
+        ("steps", C.c_int32),
+        ("chains", C.c_int32),
+        ("step_type", C.c_int32),
+        ("reserved", C.c_int32),
+        ("replay_words", C.c_void_p),
+        ("replay_len", C.c_int64),
+        ("rng_words_hint", C.c_int64),
+    ]
+
+
 class AssembleParams(C.Structure):
     _fields_ = [
         ("steps", C.c_int32),
@@ -138,7 +150,7 @@ SYMBOLS = [
     "mchb_last_kernel_launches", "mchb_stream", "mchb_sm_count", "mchb_mt19937_words",
     "mchb_genotype_rank", "mchb_genotype_unrank", "mchb_log_likelihood_batch",
     "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
-    "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch",
+    "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
 ]
 
 
@@ -202,6 +214,11 @@ def load():
         L.mchb_genotype_posteriors_batch.restype = C.c_int
         L.mchb_genotype_posteriors_batch.argtypes = [
             vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_int64,
+        ]
+        L.mchb_call_mcmc_batch.restype = C.c_int
+        L.mchb_call_mcmc_batch.argtypes = [
+            vp, C.c_int, C.POINTER(CallMcmcParams), vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
+            vp, C.c_int64, vp, C.c_int32, vp, C.c_int64, vp, C.c_int64, vp,
         ]
         _lib = L
         return _lib

@@ -202,6 +202,31 @@ class Device:
             1 if is32 else 0, gl_total, _ptr(gp), _ptr(of), _ptr(oc), _ptr(oo), hap_total))
         return gp[:gl_total], of, oc, oo
 
+    # ------------------------------------------------------------------ K5
+    def call_mcmc(self, batch, steps, chains, step_type, initial=None, pstride=0, replay_words=None):
+        """calling/classes.py:49-124 for a CallBatch whose items carry seeds (reserved) and output
+        offsets (gl_off / hap_out_off) -> dict(alleles int32, llks f64, results)."""
+        n = batch.n
+        per = chains * steps
+        a_len = int(per * batch.items["ploidy"].astype(np.int64).sum())
+        l_len = per * n
+        alleles = np.zeros(max(a_len, 1), dtype=np.int32)
+        llks = np.zeros(max(l_len, 1), dtype=np.float64)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        p = L.CallMcmcParams()
+        p.steps, p.chains, p.step_type = int(steps), int(chains), int(step_type)
+        rw = None if replay_words is None else np.ascontiguousarray(replay_words, dtype=np.uint32)
+        p.replay_words = None if rw is None else rw.ctypes.data
+        p.replay_len = 0 if rw is None else rw.size
+        p.rng_words_hint = 0
+        ini = None if initial is None else np.ascontiguousarray(initial, dtype=np.int32)
+        self._check(self._lib.mchb_call_mcmc_batch(
+            self._h, L.MEM_HOST, C.byref(p), _ptr(batch.items), n, _ptr(batch.reads), batch.reads.size,
+            _ptr(batch.counts), 0 if batch.counts is None else batch.counts.size, _ptr(batch.haps), batch.haps.size,
+            _ptr(batch.freqs), 0 if batch.freqs is None else batch.freqs.size, _ptr(ini), int(pstride),
+            _ptr(alleles), a_len, _ptr(llks), l_len, _ptr(results)))
+        return dict(alleles=alleles, llks=llks, results=results)
+
     # ------------------------------------------------------------------ K2
     def assemble_call(self, items, params, reads, counts, n_alleles, initial, out_genotypes, out_llks,
                       lens, mem=L.MEM_HOST, keepalive=()):

@@ -289,27 +289,34 @@ struct AsmCtx {
         }
     }
 
-    // log-likelihood of state slot s with haplotype hA (and hB) replaced by the given product
-    // vectors (likelihood.py:45-68 order: sum over h in order, log, * count, sum over reads)
-    __device__ __forceinline__ double eval_llk(int s, int hA, const double (&qa)[CH], int hB,
-                                               const double (&qb)[CH]) {
+    // log-likelihood of state slot s from its cached product rows (likelihood.py:45-68 order:
+    // sum over h in order, log, * count, sum over reads)
+    __device__ __forceinline__ double eval_llk(int s) {
         double acc = 0.0;
         const double *qq = q() + (size_t)(s * P) * UPAD + lane;
         const double *cn = cnt() + lane;
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) {
             double rp = 0.0;
-#pragma unroll 2
-            for (int h = 0; h < P; h++) {
-                double v = qq[h * UPAD + ch * 32];
-                v = (h == hA) ? qa[ch] : v;
-                v = (h == hB) ? qb[ch] : v;
-                rp += v;
-            }
+#pragma unroll 4
+            for (int h = 0; h < P; h++) rp += qq[h * UPAD + ch * 32];
             acc += log(rp) * cn[ch * 32];
         }
         evals++;
         return warp_sum(acc);
+    }
+
+    // swap the product row of haplotype h of slot s with the vector held in registers: used to
+    // install a proposal before evaluating it and to restore the old row on rejection (each lane
+    // touches only its own column, so no warp synchronisation is needed)
+    __device__ __forceinline__ void swap_row(int s, int h, double (&v)[CH]) {
+        double *row = q() + (size_t)(s * P + h) * UPAD + lane;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+            const double old = row[ch * 32];
+            row[ch * 32] = v[ch];
+            v[ch] = old;
+        }
     }
 
     __device__ __forceinline__ void commit(int s, int h, uint64_t k, const double (&qa)[CH]) {
@@ -317,18 +324,6 @@ struct AsmCtx {
         double *row = q() + (size_t)(s * P + h) * UPAD + lane;
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) row[ch * 32] = qa[ch];
-    }
-
-    // copies of key kh among the haplotypes ks with haplotype hs replaced by kh
-    // (jitutils.count_haplotype_copies 349-374)
-    __device__ __forceinline__ int count_copies(const uint64_t *ks, int hs, uint64_t kh) const {
-        int c = 0;
-#pragma unroll 2
-        for (int i = 0; i < P; i++) {
-            uint64_t k = (i == hs) ? kh : ks[i];
-            c += (k == kh);
-        }
-        return c;
     }
 
     // prior of the haplotype keys of a slot with up to two haplotypes replaced
@@ -363,33 +358,49 @@ struct AsmCtx {
         const int shift = B * j;
         const uint64_t clr = ~((uint64_t)amask << shift);
         const int cur = (int)((uint32_t)(kh >> shift) & amask);
-        const double lhap = LOG_INT[count_copies(ks, -1, kh)];
+        // lanes 0..P-1 compare one haplotype each (jitutils.count_haplotype_copies 349-374)
+        const bool mine = lane < P;
+        const uint64_t myk = mine ? ks[lane] : 0ull;
+        const double lhap = LOG_INT[__popc(__ballot_sync(MCHB_FULL, mine && myk == kh))];
         double lprior = 0.0;
         if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
         double qn[CH];
         if (n_all == 2 && cur < 2) {
             // bi-allelic position: one proposal; identical arithmetic to the general path below
-            // (log(n_options) = log(1) = 0, exp(-inf) = 0 for the current allele)
+            // (log(n_options) = log(1) = 0, exp(-inf) = 0 for the current allele).  The uniform
+            // is the only draw of the step, so drawing it first does not change the stream.
+            const double u = ws.next_double(lane);
             const uint64_t kn = (kh & clr) | ((uint64_t)(cur ^ 1) << shift);
             hap_products(kn, qn);
-            const double llk_o = eval_llk(s, h, qn, -1, qn);
+            swap_row(s, h, qn);  // install the proposal, qn now holds the old row
+            const double llk_o = eval_llk(s);
             double lprior_ratio = 0.0;
             if (PRIOR) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - lprior;
-            const double lprop = LOG_INT[count_copies(ks, h, kn)] - lhap;
+            const int copies_n = 1 + __popc(__ballot_sync(MCHB_FULL, mine && lane != h && myk == kn));
+            const double lprop = LOG_INT[copies_n] - lhap;
             const double mh = ((llk_o - llk) + lprior_ratio) * temp + lprop;
-            const double p_o = exp(np_minimum0(mh) - 0.0);
-            const double p_c = 1 - p_o;  // 1 - (0 + p_o)
-            const double cs0 = cur == 0 ? p_c : p_o;
-            const double cs1 = cs0 + (cur == 0 ? p_o : p_c);
-            const double u = ws.next_double(lane);
-            const int choice = (cs1 <= u) ? 2 : ((cs0 <= u) ? 1 : 0);
+            const double la = np_minimum0(mh);
+            int choice;
+            if (la < -40.0 && u >= 1.1102230246251565e-16) {
+                // exp(la) < 2^-54: 1 - p rounds to 1 and p <= u, so the search returns `cur`
+                // whatever p is; skipping exp() leaves the outcome bit-identical
+                choice = cur;
+            } else {
+                const double p_o = exp(la - 0.0);
+                const double p_c = 1 - p_o;  // 1 - (0 + p_o)
+                const double cs0 = cur == 0 ? p_c : p_o;
+                const double cs1 = cs0 + (cur == 0 ? p_o : p_c);
+                choice = (cs1 <= u) ? 2 : ((cs0 <= u) ? 1 : 0);
+            }
             if (choice >= 2) {
                 err = MCHB_ITEM_CHOICE_RANGE;
                 return;
             }
             if (choice != cur) {
-                commit(s, h, kn, qn);
+                ks[h] = kn;
                 llk = llk_o;
+            } else {
+                swap_row(s, h, qn);  // rejected: put the old row back
             }
             return;
         }
@@ -404,12 +415,15 @@ struct AsmCtx {
                 n_options++;
                 const uint64_t kn = (kh & clr) | ((uint64_t)i << shift);
                 hap_products(kn, qn);
-                const double llk_i = eval_llk(s, h, qn, -1, qn);
+                swap_row(s, h, qn);
+                const double llk_i = eval_llk(s);
+                swap_row(s, h, qn);
                 ol[i] = llk_i;
                 const double llk_ratio = llk_i - llk;
                 double lprior_ratio = 0.0;
                 if (PRIOR) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - lprior;
-                const double lprop = LOG_INT[count_copies(ks, h, kn)] - lhap;
+                const int copies_n = 1 + __popc(__ballot_sync(MCHB_FULL, mine && lane != h && myk == kn));
+                const double lprop = LOG_INT[copies_n] - lhap;
                 const double mh = (llk_ratio + lprior_ratio) * temp + lprop;
                 op[i] = np_minimum0(mh);
             }
@@ -479,35 +493,80 @@ struct AsmCtx {
         const int n_options = structural_options(lin, lout, P, step_type, o0, o1);
         __syncwarp();
         if (n_options == 0) return;  // no draw (structural.py:504-506)
+        const double u = ws.next_double(lane);  // the step's only draw (random_choice at the end)
         const double log_proposal = LOG_INV_INT[n_options];
         double lprior = 0.0;
         if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
-        double *ol = oll(), *op = opr();
-        double qa[CH], qb[CH];
-#pragma unroll 1
-        for (int i = 0; i < n_options; i++) {
-            const int h0 = o0[i], h1 = o1[i];
-            const uint64_t k0 = ks[h0], k1 = ks[h1];
-            const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
-            uint64_t lin_o = nib_set(lin, h0, nib(lin, h1));
-            int hB = -1;
-            hap_products(k0n, qa);
-            if (step_type == 0) {
-                const uint64_t k1n = (k0 & mask_in) | (k1 & ~mask_in);
-                lin_o = nib_set(lin_o, h1, nib(lin, h0));
-                hap_products(k1n, qb);
-                hB = h1;
-            }
-            const double llk_i = eval_llk(s, h0, qa, hB, qb);
-            ol[i] = llk_i;
-            const double llk_ratio = llk_i - llk;
-            double lprior_ratio = 0.0;
-            if (PRIOR) lprior_ratio = prior_of_labels(lin_o, lout) - lprior;
-            const int n_return = structural_options(lin_o, lout, P, step_type, nullptr, nullptr);
-            const double lprop = LOG_INV_INT[n_return] - log_proposal;
-            const double mh = (llk_ratio + lprior_ratio) * temp + lprop;
-            op[i] = np_minimum0(mh);
+        // lane i owns option i: its label matrix and its number of reverse moves are evaluated by
+        // all lanes at once (the option functions are pure integer code)
+        uint64_t my_lin = lin;
+        if (lane < n_options) {
+            const int h0 = o0[lane], h1 = o1[lane];
+            my_lin = nib_set(lin, h0, nib(lin, h1));
+            if (step_type == 0) my_lin = nib_set(my_lin, h1, nib(lin, h0));
         }
+        int my_return = 1;
+        double my_la = -INFINITY;
+#pragma unroll 1
+        for (int base = 0; base < n_options; base += 32) {
+            // (more than 32 options only for ploidy > 6: processed in rounds of 32)
+            uint64_t lin_r = my_lin;
+            if (base > 0) {
+                lin_r = lin;
+                if (base + lane < n_options) {
+                    const int h0 = o0[base + lane], h1 = o1[base + lane];
+                    lin_r = nib_set(lin, h0, nib(lin, h1));
+                    if (step_type == 0) lin_r = nib_set(lin_r, h1, nib(lin, h0));
+                }
+            }
+            const int n_ret = structural_options(lin_r, lout, P, step_type, nullptr, nullptr);
+            const int rounds = min(32, n_options - base);
+#pragma unroll 1
+            for (int k = 0; k < rounds; k++) {
+                const int i = base + k;
+                const int h0 = o0[i], h1 = o1[i];
+                const uint64_t k0 = ks[h0], k1 = ks[h1];
+                const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
+                const uint64_t lin_o = __shfl_sync(MCHB_FULL, lin_r, k);
+                const int n_return = __shfl_sync(MCHB_FULL, n_ret, k);
+                double qa[CH], qb[CH];
+                hap_products(k0n, qa);
+                swap_row(s, h0, qa);
+                if (step_type == 0) {
+                    const uint64_t k1n = (k0 & mask_in) | (k1 & ~mask_in);
+                    hap_products(k1n, qb);
+                    swap_row(s, h1, qb);
+                }
+                const double llk_i = eval_llk(s);
+                swap_row(s, h0, qa);
+                if (step_type == 0) swap_row(s, h1, qb);
+                double lprior_ratio = 0.0;
+                if (PRIOR) lprior_ratio = prior_of_labels(lin_o, lout) - lprior;
+                const double lprop = LOG_INV_INT[n_return] - log_proposal;
+                const double mh = ((llk_i - llk) + lprior_ratio) * temp + lprop;
+                const double la = np_minimum0(mh);
+                if (i < 32) {
+                    if (lane == i) {
+                        my_la = la;
+                        my_return = n_return;
+                    }
+                }
+                oll()[i] = llk_i;
+                opr()[i] = la;
+            }
+        }
+        (void)my_return;
+        double *ol = oll(), *op = opr();
+        // all proposals hopeless (exp(la) < 2^-54 each) and u > 0: the cumulative sums stay below
+        // u until the final "stay" slot, so the outcome is "stay" without evaluating exp()
+        bool hopeless = u >= 1.1102230246251565e-16;
+        if (n_options <= 32) {
+            hopeless = hopeless && __all_sync(MCHB_FULL, lane >= n_options || my_la < -40.0);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < n_options; i++) hopeless = hopeless && (op[i] < -40.0);
+        }
+        if (hopeless) return;
         ol[n_options] = -INFINITY;
         op[n_options] = -INFINITY;
         const double ln_opts = LOG_INT[n_options];
@@ -519,14 +578,22 @@ struct AsmCtx {
             sum += p;
         }
         op[n_options] = 1 - sum;
-        const int choice = random_choice_inplace(op, n_options + 1);
+        double acc = 0.0;
+#pragma unroll 1
+        for (int i = 0; i <= n_options; i++) {
+            acc += op[i];
+            op[i] = acc;
+        }
+        const int choice = searchsorted_right(op, n_options + 1, u);
         if (choice < n_options) {
             const int h0 = o0[choice], h1 = o1[choice];
             const uint64_t k0 = ks[h0], k1 = ks[h1];
             const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
+            double qa[CH];
             hap_products(k0n, qa);
             if (step_type == 0) {
                 const uint64_t k1n = (k0 & mask_in) | (k1 & ~mask_in);
+                double qb[CH];
                 hap_products(k1n, qb);
                 commit(s, h1, k1n, qb);
             }
@@ -920,8 +987,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
                         for (int t = 0; t < T; t++) c.commit(t, h, k, qn);
                     }
                     __syncwarp();
-                    // one base step on a non-existent haplotype index evaluates the current state
-                    double llk0 = c.eval_llk(0, -1, qn, -1, qn);
+                    double llk0 = c.eval_llk(0);
                     c.evals--;  // the initial evaluation is not a proposal
 #pragma unroll 1
                     for (int t = 0; t < T; t++) lt[t] = llk0;
@@ -971,7 +1037,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
                 }
             }
             status = c.err;
-            if (!status && c.ws.exhausted) status = MCHB_ITEM_RNG_EXHAUSTED;
+            if (!status && c.ws.exhausted()) status = MCHB_ITEM_RNG_EXHAUSTED;
         }
         if (lane == 0) {
             mchb_item_result r;

@@ -36,11 +36,10 @@ __constant__ float LOGF_INT[MCHB_TABLE_N];
 // ---------------------------------------------------------------------------------------
 struct WordStream {
     const uint32_t *base;
-    int64_t len;      // words available
+    int64_t len;      // words available (reads beyond it return 0 and flag exhaustion at the end)
     int64_t cur;      // words consumed so far (uniform)
     uint32_t w_cur;   // lane's word of block cur/32
     uint32_t w_next;  // lane's word of block cur/32 + 1
-    int exhausted;
 
     __device__ __forceinline__ uint32_t load_block(int64_t blk, int lane) const {
         int64_t i = blk * 32 + lane;
@@ -50,14 +49,13 @@ struct WordStream {
         base = b;
         len = n;
         cur = 0;
-        exhausted = 0;
         w_cur = load_block(0, lane);
         w_next = load_block(1, lane);
     }
+    __device__ __forceinline__ bool exhausted() const { return cur > len; }
     __device__ __forceinline__ uint32_t next_u32(int lane) {
-        int k = (int)(cur & 31);
-        uint32_t w = __shfl_sync(MCHB_FULL, w_cur, k);
-        if (cur >= len) exhausted = 1;
+        const int k = (int)cur & 31;
+        const uint32_t w = __shfl_sync(MCHB_FULL, w_cur, k);
         cur++;
         if (k == 31) {
             w_cur = w_next;
@@ -71,15 +69,14 @@ struct WordStream {
         uint32_t b = next_u32(lane) >> 6;
         return ((double)b + (double)a * 67108864.0) / 9007199254740992.0;
     }
-    // randomimpl.py:454-520 _randrange_impl (state "np", n <= 2^31 here); n == 1 draws nothing
+    // randomimpl.py:454-520 _randrange_impl (state "np", n <= 2^31 here); n == 1 draws nothing.
+    // Past the end of the stream the words are 0, which ends the rejection loop.
     __device__ __forceinline__ int randint(int n, int lane) {
         if (n == 1) return 0;
-        int nbits = 32 - __clz(n - 1);
-        uint32_t mask = 0xffffffffu >> (32 - nbits);
+        const uint32_t mask = 0xffffffffu >> __clz(n - 1);
         for (;;) {
             uint32_t r = next_u32(lane) & mask;
             if ((int)r < n) return (int)r;
-            if (exhausted) return 0;
         }
     }
 };

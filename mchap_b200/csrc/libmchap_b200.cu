@@ -15,6 +15,7 @@
 #include "aux_kernels.cuh"
 #include "assemble_kernel.cuh"
 #include "exact_kernel.cuh"
+#include "call_mcmc_kernel.cuh"
 
 using namespace mchb;
 
@@ -41,7 +42,7 @@ namespace {
 enum Slot {
     S_ITEMS = 0, S_ORDER, S_READS, S_COUNTS, S_NALLELES, S_INITIAL, S_OUT_G, S_OUT_L, S_RESULTS,
     S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
-    S_HAPS, S_FREQS, S_SCRATCH, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS,
+    S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS,
     S_NSLOTS
 };
 
@@ -116,6 +117,10 @@ int init_tables(mchb_handle *h) {
     CK(cudaMemcpyToSymbol(LOG_INV_INT, log_inv, sizeof(log_inv)));
     CK(cudaMemcpyToSymbol(LGAMMA_INT, lgam, sizeof(lgam)));
     CK(cudaMemcpyToSymbol(LOGF_INT, logf_int, sizeof(logf_int)));
+    static double log_ratio[17 * 17];
+    for (int i = 0; i < 17; i++)
+        for (int j = 0; j < 17; j++) log_ratio[i * 17 + j] = (i > 0 && j > 0) ? std::log((double)i / (double)j) : 0.0;
+    CK(cudaMemcpyToSymbol(LOG_RATIO, log_ratio, sizeof(log_ratio)));
     if (h->device < 64) g_tables_ready[h->device] = true;
     return MCHB_OK;
 }
@@ -881,3 +886,161 @@ int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------ K5 call MCMC
+extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcmc_params *params,
+                                    const mchb_call_item *items, int64_t n_items, const double *reads,
+                                    int64_t reads_len, const int64_t *counts, int64_t counts_len,
+                                    const int8_t *haplotypes, int64_t haplotypes_len, const double *freqs,
+                                    int64_t freqs_len, const int32_t *initial, int32_t pstride, int32_t *out_alleles,
+                                    int64_t out_alleles_len, double *out_llks, int64_t out_llks_len,
+                                    mchb_item_result *results) {
+    if (!h || !params || !items || !results || n_items < 0 || !out_alleles || !out_llks) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    if (n_items > 0x7fffffff) {
+        h->err = "too many items in one call";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const mchb_call_mcmc_params &pp = *params;
+    if (pp.steps < 0 || pp.chains < 0 || (pp.step_type != 0 && pp.step_type != 1)) {
+        h->err = "bad call-mcmc parameters";
+        return MCHB_ERR_ARGUMENT;
+    }
+    CallGeom g;
+    int rc = check_call_items(h, items, n_items, reads_len, counts != nullptr, counts_len, haplotypes_len,
+                              freqs != nullptr, freqs_len, -1, -1, true, g);
+    if (rc) return rc;
+    std::map<uint32_t, int32_t> seed_index;
+    std::vector<uint32_t> seeds;
+    std::vector<int32_t> item_stream((size_t)n_items, 0), order;
+    int64_t words_needed = 0;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_call_item &it = items[i];
+        const int64_t tsz = (int64_t)pp.chains * pp.steps * it.ploidy;
+        if (it.gl_off < 0 || it.gl_off + tsz > out_alleles_len || it.hap_out_off < 0 ||
+            it.hap_out_off + (int64_t)pp.chains * pp.steps > out_llks_len || (initial && pstride < it.ploidy)) {
+            h->err = "call-mcmc item " + std::to_string(i) + " exceeds the output array lengths";
+            return MCHB_ERR_ARGUMENT;
+        }
+        results[i].status = MCHB_ITEM_OK;
+        results[i].n_het = 0;
+        results[i].rng_words = 0;
+        results[i].llk_evals = 0;
+        order.push_back((int32_t)i);
+        if (!pp.replay_words) {
+            const uint32_t seed = (uint32_t)it.reserved;
+            auto f = seed_index.find(seed);
+            if (f == seed_index.end()) {
+                f = seed_index.emplace(seed, (int32_t)seeds.size()).first;
+                seeds.push_back(seed);
+            }
+            item_stream[(size_t)i] = f->second;
+        }
+        words_needed = std::max(words_needed, (int64_t)pp.chains * pp.steps * (4 * (int64_t)it.ploidy + 8) + 64);
+    }
+    const size_t per_warp =
+        (((size_t)g.umax * g.hmax + g.umax + 2 * (size_t)g.hmax + (size_t)g.hmax * (g.pmax + 2)) * 8 + 3 * (size_t)g.pmax * 4 + 15) &
+        ~(size_t)15;
+    int warps_per_cta = 4;
+    while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
+    if (per_warp * warps_per_cta > (size_t)h->smem_optin) {
+        h->err = "call-mcmc item needs more shared memory than one CTA can have";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const size_t smem = per_warp * warps_per_cta;
+    void *ditems, *dstream, *dcounter, *dresults, *dorder;
+    if ((rc = ensure(h, S_ITEMS, sizeof(mchb_call_item) * (size_t)n_items, &ditems))) return rc;
+    if ((rc = ensure(h, S_STREAM, sizeof(int32_t) * (size_t)n_items, &dstream))) return rc;
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8, &dcounter))) return rc;
+    if ((rc = ensure(h, S_RESULTS, sizeof(mchb_item_result) * (size_t)n_items, &dresults))) return rc;
+    if ((rc = ensure(h, S_ORDER, sizeof(int32_t) * (size_t)n_items, &dorder))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_call_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dstream, item_stream.data(), sizeof(int32_t) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dresults, results, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    const double *dreads, *dfreqs;
+    const int64_t *dcounts;
+    const int8_t *dhaps;
+    const int32_t *dinit;
+    int32_t *doa;
+    double *dol;
+    if ((rc = stage_in(h, mem, S_READS, reads, reads_len, &dreads))) return rc;
+    if ((rc = stage_in(h, mem, S_COUNTS, counts, counts_len, &dcounts))) return rc;
+    if ((rc = stage_in(h, mem, S_HAPS, haplotypes, haplotypes_len, &dhaps))) return rc;
+    if ((rc = stage_in(h, mem, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
+    if ((rc = stage_in(h, mem, S_INIT32, initial, initial ? n_items * pstride : 0, &dinit))) return rc;
+    if ((rc = stage_out(h, mem, S_OUT_A32, out_alleles, out_alleles_len, &doa))) return rc;
+    if ((rc = stage_out(h, mem, S_OUT_L, out_llks, out_llks_len, &dol))) return rc;
+    CK(cudaFuncSetAttribute(call_mcmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, call_mcmc_kernel, warps_per_cta * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int64_t stream_len = pp.rng_words_hint > 0 ? pp.rng_words_hint : words_needed;
+    if (pp.replay_words) stream_len = pp.replay_len;
+    stream_len = (stream_len + 31) & ~(int64_t)31;
+    std::vector<int32_t> todo = order;
+    for (int attempt = 0; attempt < 6 && !todo.empty(); attempt++) {
+        uint32_t *dwords = nullptr;
+        if (pp.replay_words) {
+            void *p;
+            if ((rc = ensure(h, S_WORDS, sizeof(uint32_t) * (size_t)stream_len, &p))) return rc;
+            CK(cudaMemsetAsync(p, 0, sizeof(uint32_t) * (size_t)stream_len, h->stream));
+            CK(cudaMemcpyAsync(p, pp.replay_words, sizeof(uint32_t) * (size_t)pp.replay_len, cudaMemcpyHostToDevice, h->stream));
+            dwords = (uint32_t *)p;
+        } else {
+            if ((rc = fill_streams(h, seeds, stream_len, &dwords))) return rc;
+        }
+        CK(cudaMemcpyAsync(dorder, todo.data(), sizeof(int32_t) * todo.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+        CallMcmcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.items = (const mchb_call_item *)ditems;
+        a.order = (const int32_t *)dorder;
+        a.n_order = (int32_t)todo.size();
+        a.reads = dreads;
+        a.counts = dcounts;
+        a.haplotypes = dhaps;
+        a.freqs = dfreqs;
+        a.initial = dinit;
+        a.pstride = pstride;
+        a.out_alleles = doa;
+        a.out_llks = dol;
+        a.results = (mchb_item_result *)dresults;
+        a.words = dwords;
+        a.item_stream = (const int32_t *)dstream;
+        a.stream_len = pp.replay_words ? pp.replay_len : stream_len;
+        a.steps = pp.steps;
+        a.chains = pp.chains;
+        a.step_type = pp.step_type;
+        a.work_counter = (int32_t *)dcounter;
+        a.umax = g.umax;
+        a.hmax = g.hmax;
+        a.pmax = g.pmax;
+        a.smem_per_warp = (int32_t)per_warp;
+        long long want = ((long long)todo.size() + warps_per_cta - 1) / warps_per_cta;
+        long long grid = std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
+        CK(cudaEventRecord(h->ev0, h->stream));
+        call_mcmc_kernel<<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev1, h->stream));
+        h->launches++;
+        CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->kernel_ms += ms;
+        if (pp.replay_words) break;
+        std::vector<int32_t> next;
+        for (int32_t id : todo)
+            if (results[id].status == MCHB_ITEM_RNG_EXHAUSTED) next.push_back(id);
+        todo.swap(next);
+        stream_len *= 2;
+    }
+    if (mem == MCHB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_alleles, doa, sizeof(int32_t) * (size_t)out_alleles_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_llks, dol, sizeof(double) * (size_t)out_llks_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return MCHB_OK;
+}

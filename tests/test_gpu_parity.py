@@ -233,3 +233,138 @@ def test_edge_cases(dev):
     with pytest.raises(NotImplementedError):
         DenovoMCMC(ploidy=2, n_alleles=[2] * 70, steps=5, chains=1, random_seed=1, fix_homozygous=2.0).fit(
             np.full((3, 70, 2), 0.5))
+
+
+# ----------------------------------------------------------------------------- call-exact (K4)
+def _prior(golden, k, meta, name):
+    if meta["inbreeding"] is None:
+        return None
+    return (meta["inbreeding"], golden["%s%d_freqs" % (name, k)] if meta["with_freqs"] else None)
+
+
+def test_call_exact_golden(dev, golden):
+    """posterior_mode / genotype_likelihoods / genotype_posteriors against reference fixtures:
+    mode alleles and VCF-order indices bit-exact, float64 statistics to 1e-9, float32 GL exact or
+    1 ulp (CUDA vs glibc log)."""
+    from mchap_b200.calling import exact
+
+    for k in range(golden.meta["exact_cases"]):
+        meta = golden.meta["exact%d" % k]
+        reads = golden["exact%d_reads" % k]
+        counts = golden["exact%d_counts" % k]
+        haps = golden["exact%d_haplotypes" % k]
+        prior = _prior(golden, k, meta, "exact")
+        P, H = meta["P"], meta["H"]
+        mode, llk, prob, support, freqs, occur = exact.posterior_mode(
+            reads, P, haps, read_counts=counts, prior=prior, return_support_prob=True,
+            return_posterior_frequencies=True, return_posterior_occurrence=True)
+        np.testing.assert_array_equal(mode, golden["exact%d_mode" % k], err_msg="case %d" % k)
+        close([llk, prob, support], golden["exact%d_scalars" % k])
+        close(freqs, golden["exact%d_mode_freqs" % k], rtol=1e-9)
+        close(occur, golden["exact%d_mode_occur" % k], rtol=1e-9)
+        gl = exact.genotype_likelihoods(reads, P, haps, read_counts=counts)
+        assert gl.dtype == np.float32 and len(gl) == golden["exact%d_ngen" % k][0]
+        np.testing.assert_allclose(gl, golden["exact%d_gl" % k], rtol=2e-7, atol=0)
+        # posteriors from the REFERENCE's float32 GL array: isolates genotype_posteriors
+        gp = exact.genotype_posteriors(golden["exact%d_gl" % k], P, H, prior=prior)
+        np.testing.assert_allclose(gp, golden["exact%d_gp" % k], rtol=1e-9, atol=1e-300)
+        assert int(np.argmax(gp)) == int(np.argmax(golden["exact%d_gp" % k]))
+        fr = exact.posterior_allele_frequencies(golden["exact%d_gp" % k], P, H)
+        np.testing.assert_allclose(np.stack(fr), golden["exact%d_fr" % k], rtol=1e-9, atol=1e-300)
+        alt_g, alt_p = exact.alternate_dosage_posteriors(golden["exact%d_mode" % k], golden["exact%d_gp" % k])
+        np.testing.assert_array_equal(alt_g, golden["exact%d_alt_g" % k])
+        np.testing.assert_array_equal(alt_p, golden["exact%d_alt_p" % k])
+
+
+@pytest.mark.parametrize("ploidy,n_haps,n_pos,prior_kind", [
+    (6, 8, 8, None),          # BASELINE configs[2] shape: 1716 genotypes
+    (6, 8, 8, "flat"),
+    (4, 32, 8, "freqs"),      # configs[4] panel: 52360 genotypes
+    (2, 5, 3, "freqs0"),
+    (8, 4, 6, "flat"),
+])
+def test_call_exact_batch_vs_oracle(dev, oracle, ploidy, n_haps, n_pos, prior_kind):
+    from mchap_b200.calling import exact
+    from mchap_b200.synth import synth_haplotype_panel
+
+    n_items = 6 if n_haps == 32 else 16
+    batch, panels, truth = synth_haplotype_panel(n_items, n_haps, n_pos, ploidy, depth=40, seed=ploidy + n_haps)
+    rng = np.random.default_rng(1)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    haps = [panels[i] for i in range(n_items)]
+    priors = None
+    if prior_kind is not None:
+        priors = []
+        for i in range(n_items):
+            f = rng.random(n_haps) + 0.1
+            f /= f.sum()
+            priors.append({"flat": (0.1, None), "freqs": (0.2, f), "freqs0": (0.0, f)}[prior_kind])
+    res = exact.posterior_mode_batch(reads, ploidy, haps, counts, priors)
+    gls = exact.genotype_likelihoods_batch(reads, ploidy, haps, counts)
+    for i in range(n_items):
+        pr = None if priors is None else priors[i]
+        want = oracle.posterior_mode(reads[i], ploidy, haps[i], counts[i], pr, True, True, True)
+        got = res[i]
+        np.testing.assert_array_equal(got[0], want[0], err_msg="item %d" % i)
+        close([got[1], got[2], got[3]], [want[1], want[2], want[3]])
+        close(got[4], want[4], rtol=1e-9)
+        close(got[5], want[5], rtol=1e-9)
+        gl64 = oracle.genotype_likelihoods(reads[i], ploidy, haps[i], counts[i], dtype=np.float64)
+        np.testing.assert_allclose(gls[i], gl64.astype(np.float32), rtol=2e-7, atol=0)
+        # size-independent properties at full enumeration size
+        assert abs(got[4].sum() - 1.0) < 1e-9
+        assert got[2] <= got[3] + 1e-12 <= 1.0 + 1e-9
+
+
+# ----------------------------------------------------------------------------- call MCMC (K5)
+def test_calling_mcmc_golden(dev, golden):
+    """CallingMCMC.fit against reference fixtures: identical genotype traces, greedy start, llks."""
+    from mchap_b200 import CallingMCMC
+
+    for k in range(golden.meta["call_cases"]):
+        meta = golden.meta["call%d" % k]
+        reads = golden["call%d_reads" % k]
+        counts = golden["call%d_counts" % k]
+        haps = golden["call%d_haplotypes" % k]
+        prior = _prior(golden, k, meta, "call")
+        model = CallingMCMC(ploidy=meta["P"], haplotypes=haps, prior=prior, steps=meta["steps"],
+                            chains=meta["chains"], random_seed=meta["seed"], step_type=meta["step_type"])
+        trace = model.fit(reads, read_counts=counts)
+        np.testing.assert_array_equal(trace.genotypes, golden["call%d_genotypes" % k], err_msg="case %d" % k)
+        close(trace.llks, golden["call%d_llks" % k])
+        assert trace.n_allele == len(haps)
+
+
+@pytest.mark.parametrize("ploidy,n_haps,step_type,prior_kind", [
+    (4, 32, "Gibbs", None),           # BASELINE configs[4] shape
+    (4, 32, "Gibbs", "freqs"),
+    (6, 8, "Gibbs", "flat"),
+    (4, 8, "Metropolis-Hastings", "freqs"),
+    (2, 40, "Gibbs", None),           # more than one round of 32 candidate alleles
+])
+def test_calling_mcmc_batch_vs_oracle(dev, oracle, ploidy, n_haps, step_type, prior_kind):
+    from mchap_b200 import CallingMCMC
+    from mchap_b200.synth import synth_haplotype_panel
+
+    n_items, steps = 10, 80
+    batch, panels, truth = synth_haplotype_panel(n_items, n_haps, 8, ploidy, depth=40, seed=3 * ploidy + n_haps)
+    rng = np.random.default_rng(2)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    haps = [panels[i] for i in range(n_items)]
+    priors = None
+    if prior_kind is not None:
+        priors = []
+        for i in range(n_items):
+            f = rng.random(n_haps) + 0.1
+            f /= f.sum()
+            priors.append({"flat": (0.15, None), "freqs": (0.2, f)}[prior_kind])
+    model = CallingMCMC(ploidy=ploidy, haplotypes=None, steps=steps, chains=2, random_seed=5, step_type=step_type)
+    traces, results = model.fit_batch(reads, counts, haplotypes_list=haps, priors=priors, return_results=True)
+    for i in range(n_items):
+        ref = oracle.calling_fit(reads[i], counts[i], ploidy, haps[i], prior=None if priors is None else priors[i],
+                                 steps=steps, chains=2, random_seed=5, step_type=step_type)
+        np.testing.assert_array_equal(traces[i].genotypes, ref["genotypes"], err_msg="item %d" % i)
+        close(traces[i].llks, ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
