@@ -42,6 +42,8 @@ def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    if os.environ.get("MCHB_ASM_MINBLOCKS"):
+        extra_flags = list(extra_flags) + ["-DMCHB_ASM_MINBLOCKS=" + os.environ["MCHB_ASM_MINBLOCKS"]]
     cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + [
         "-o", LIB_PATH, os.path.join(CSRC, "libmchap_b200.cu"),
     ]

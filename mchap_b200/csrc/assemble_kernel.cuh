@@ -25,6 +25,11 @@
 #pragma once
 #include "common.cuh"
 
+// resident CTAs per SM the register allocation is tuned for (4 warps per CTA)
+#ifndef MCHB_ASM_MINBLOCKS
+#define MCHB_ASM_MINBLOCKS 4
+#endif
+
 namespace mchb {
 
 struct AsmArgs {
@@ -115,52 +120,69 @@ __device__ __noinline__ double snp_log_genotype_prior(uint64_t g, int P, int n_a
 // structural.py: options of a label matrix (lin = inside-interval labels, lout = outside labels,
 // nibble packed).  type 0: recombination (75-178), type 1: dosage swap (182-307).  Returns the
 // number of options; when o0 != nullptr the (h0, h1) pairs are written in the reference's order.
+// All tests are nibble-parallel bit operations on masks with one bit per haplotype (bit 4h):
+//   ff: row h is not a duplicate of an earlier row          (haplotype_dosage[h] != 0)
+//   sf: h is the first haplotype carrying its inside segment (segment_dosage[h] != 0)
+//   ss: h is the only haplotype carrying its inside segment  (segment_dosage[h] == 1)
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ int structural_options(uint64_t lin, uint64_t lout, int P, int type, uint8_t *o0,
-                                               uint8_t *o1) {
-    // bit h of ff: row h is not a duplicate of an earlier row (haplotype_dosage != 0)
-    // bit h of sf: h is the first haplotype carrying its inside segment (segment_dosage != 0)
-    // bit h of ss: h is the only haplotype carrying its inside segment (segment_dosage == 1)
-    uint32_t ff = 0, sf = 0, ss = 0;
+template <typename W>
+__device__ __forceinline__ W nib_eq(W v, int x, W ones) {
+    W t = v ^ (ones * (W)x);  // zero nibble where equal
+    t |= t >> 1;
+    t |= t >> 2;              // bit 0 of every nibble = OR of the nibble's bits
+    return ~t & ones;
+}
+
+template <typename W>
+__device__ __forceinline__ int structural_options_w(W lin, W lout, int P, int type, uint8_t *o0, uint8_t *o1) {
+    const W all = (4 * P >= (int)(8 * sizeof(W))) ? ~(W)0 : ((((W)1) << (4 * P)) - 1);
+    const W ones = (W)0x1111111111111111ull & all;
+    W ff = 0, sf = 0, ss = 0;
 #pragma unroll 1
     for (int h = 0; h < P; h++) {
-        const int li = nib(lin, h), lo = nib(lout, h);
-        bool dup_full = false, dup_seg = false;
-        int c = 0;
-#pragma unroll 1
-        for (int k = 0; k < P; k++) {
-            const bool eq = nib(lin, k) == li;
-            c += eq;
-            dup_seg = dup_seg || (eq && k < h);
-            dup_full = dup_full || (eq && k < h && nib(lout, k) == lo);
-        }
-        ff |= (dup_full ? 0u : 1u) << h;
-        sf |= (dup_seg ? 0u : 1u) << h;
-        ss |= (c == 1 ? 1u : 0u) << h;
+        const int sh = 4 * h;
+        const W eqI = nib_eq<W>(lin, (int)((lin >> sh) & 15), ones);
+        const W eqO = nib_eq<W>(lout, (int)((lout >> sh) & 15), ones);
+        const W bit = ((W)1) << sh;
+        const W below = bit - 1;
+        if (!(eqI & eqO & below)) ff |= bit;
+        if (!(eqI & below)) sf |= bit;
+        if (!(eqI & (eqI - 1))) ss |= bit;
     }
     int n = 0;
 #pragma unroll 1
     for (int h0 = 0; h0 < P; h0++) {
-        if (!((ff >> h0) & 1)) continue;               // duplicate copy of a haplotype
-        if (type == 1 && ((ss >> h0) & 1)) continue;   // would delete the only copy of the segment
-        const int li0 = nib(lin, h0), lo0 = nib(lout, h0);
-#pragma unroll 1
-        for (int h1 = (type == 0 ? h0 + 1 : 0); h1 < P; h1++) {
-            if (type == 0) {
-                if (!((ff >> h1) & 1)) continue;
-                if (nib(lin, h1) == li0 || nib(lout, h1) == lo0) continue;  // equivalent genotype
-            } else {
-                if (!((sf >> h1) & 1)) continue;   // donor segment already visited
-                if (nib(lin, h1) == li0) continue; // identical segment
-            }
-            if (o0) {
+        const int sh = 4 * h0;
+        const W bit = ((W)1) << sh;
+        if (!(ff & bit)) continue;               // duplicate copy of a haplotype
+        if (type == 1 && (ss & bit)) continue;   // would delete the only copy of the segment
+        const W eqI = nib_eq<W>(lin, (int)((lin >> sh) & 15), ones);
+        W cand;
+        if (type == 0) {
+            const W eqO = nib_eq<W>(lout, (int)((lout >> sh) & 15), ones);
+            cand = ff & ~eqI & ~eqO & ~((bit << 1) - 1);  // h1 > h0, both segments differ
+        } else {
+            cand = sf & ~eqI;                             // first carrier of a different segment
+        }
+        if (!o0) {
+            n += (sizeof(W) == 8) ? __popcll((unsigned long long)cand) : __popc((unsigned)cand);
+        } else {
+            while (cand) {
+                const int b = (sizeof(W) == 8) ? __ffsll((long long)cand) - 1 : __ffs((int)cand) - 1;
                 o0[n] = (uint8_t)h0;
-                o1[n] = (uint8_t)h1;
+                o1[n] = (uint8_t)(b >> 2);
+                n++;
+                cand &= cand - 1;
             }
-            n++;
         }
     }
     return n;
+}
+
+__device__ __noinline__ int structural_options(uint64_t lin, uint64_t lout, int P, int type, uint8_t *o0,
+                                               uint8_t *o1) {
+    if (P <= 8) return structural_options_w<uint32_t>((uint32_t)lin, (uint32_t)lout, P, type, o0, o1);
+    return structural_options_w<uint64_t>(lin, lout, P, type, o0, o1);
 }
 
 // structural.py:311-430 haplotype_segment_labels on packed keys: first-occurrence labels of the
@@ -218,7 +240,7 @@ struct AsmCtx {
     int lane;
     int N, A, P, B;
     uint32_t amask;
-    bool pow2;
+    bool pow2, key32;
     double invP;
     uint32_t slots;  // nibble t -> state slot (parallel tempering swaps exchange slots)
     WordStream ws;
@@ -268,16 +290,28 @@ struct AsmCtx {
     __device__ __forceinline__ void hap_products(uint64_t k, double (&out)[CH]) const {
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) out[ch] = 1.0;
-        const double *base = Rt() + lane;
-        const int stride = A * UPAD;
-#pragma unroll 2
-        for (int j = 0; j < N; j++) {
-            int al = (int)((uint32_t)k & amask);
-            k >>= B;
-            const double *p = base + al * UPAD;
+        const unsigned char *base = reinterpret_cast<const unsigned char *>(Rt() + lane);
+        const int astride = UPAD * 8;          // bytes between alleles
+        const int pstride = A * UPAD * 8;      // bytes between positions
+        if (key32) {
+            uint32_t kk = (uint32_t)k;
+#pragma unroll 4
+            for (int j = 0; j < N; j++) {
+                const double *p = reinterpret_cast<const double *>(base + (kk & amask) * astride);
+                kk >>= B;
 #pragma unroll
-            for (int ch = 0; ch < CH; ch++) out[ch] *= p[ch * 32];
-            base += stride;
+                for (int ch = 0; ch < CH; ch++) out[ch] *= p[ch * 32];
+                base += pstride;
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < N; j++) {
+                const double *p = reinterpret_cast<const double *>(base + ((uint32_t)k & amask) * astride);
+                k >>= B;
+#pragma unroll
+                for (int ch = 0; ch < CH; ch++) out[ch] *= p[ch * 32];
+                base += pstride;
+            }
         }
         if (pow2) {
 #pragma unroll
@@ -767,7 +801,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
                     double prod = isnan(v) ? 1.0 : v;
                     rp += pow2 ? prod * invP : prod / (double)P;
                 }
-                acc += log(rp) * cnt[ch * 32 + lane];
+                acc += dlog(rp) * cnt[ch * 32 + lane];
             }
             double lp = lprior + warp_sum(acc);
             denom = (i == 0) ? lp : add_log_prob(denom, lp);
@@ -778,7 +812,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
         int fixed = 0, fa = 0;
 #pragma unroll 1
         for (int al = 0; al < nA; al++) {
-            double prob = exp(homlp[al] - denom);
+            double prob = dexp(homlp[al] - denom);
             if (prob >= a.fix_homozygous) {
                 fixed = 1;
                 fa = al;
@@ -890,7 +924,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
 }
 
 template <int CH, bool PRIOR>
-__global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ AsmArgs a) {
+__global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const __grid_constant__ AsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -921,6 +955,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ A
         c.N = N;
         c.B = setup >> 16;
         c.amask = (1u << c.B) - 1u;
+        c.key32 = N * c.B <= 32;
 
         int status = 0;
         if (N == 0) {

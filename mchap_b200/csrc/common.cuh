@@ -36,25 +36,25 @@ __constant__ float LOGF_INT[MCHB_TABLE_N];
 // ---------------------------------------------------------------------------------------
 struct WordStream {
     const uint32_t *base;
-    int64_t len;      // words available (reads beyond it return 0 and flag exhaustion at the end)
-    int64_t cur;      // words consumed so far (uniform)
+    int len;          // words available (< 2^31; reads beyond it return 0 and flag exhaustion at the end)
+    int cur;          // words consumed so far (uniform)
     uint32_t w_cur;   // lane's word of block cur/32
     uint32_t w_next;  // lane's word of block cur/32 + 1
 
-    __device__ __forceinline__ uint32_t load_block(int64_t blk, int lane) const {
-        int64_t i = blk * 32 + lane;
+    __device__ __forceinline__ uint32_t load_block(int blk, int lane) const {
+        const int i = blk * 32 + lane;
         return (i < len) ? __ldg(base + i) : 0u;
     }
     __device__ __forceinline__ void init(const uint32_t *b, int64_t n, int lane) {
         base = b;
-        len = n;
+        len = (int)n;
         cur = 0;
         w_cur = load_block(0, lane);
         w_next = load_block(1, lane);
     }
     __device__ __forceinline__ bool exhausted() const { return cur > len; }
     __device__ __forceinline__ uint32_t next_u32(int lane) {
-        const int k = (int)cur & 31;
+        const int k = cur & 31;
         const uint32_t w = __shfl_sync(MCHB_FULL, w_cur, k);
         cur++;
         if (k == 31) {
@@ -80,6 +80,12 @@ struct WordStream {
         }
     }
 };
+
+// Out-of-line log / exp for code that runs once per item (set-up), to keep it small.  In the
+// steady-state loop the libdevice bodies stay inlined: sharing them through calls was measured
+// 5 % slower (round-1 profile notes in profiles/README.md).
+__device__ __noinline__ double dlog(double x) { return log(x); }
+__device__ __noinline__ double dexp(double x) { return exp(x); }
 
 // ---------------------------------------------------------------------------------------
 // log-space helpers (jitutils.py:6-74)

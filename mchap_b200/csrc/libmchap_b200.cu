@@ -525,6 +525,10 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     int64_t stream_len = pp.rng_words_hint > 0 ? pp.rng_words_hint : words_needed;
     if (pp.replay_words) stream_len = pp.replay_len;
     stream_len = (stream_len + 31) & ~(int64_t)31;
+    if (stream_len > 0x7fffff00LL) {
+        h->err = "random word stream longer than 2^31 words: split the batch into fewer steps per call";
+        return MCHB_ERR_ARGUMENT;
+    }
     std::vector<int32_t> todo[NCLS];
     for (int c = 0; c < NCLS; c++) todo[c] = order[c];
     for (int attempt = 0; attempt < 6; attempt++) {
