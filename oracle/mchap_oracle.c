@@ -672,6 +672,10 @@ double orc_log_genotype_allele_prior(const int64_t *g, int P, int variable_allel
 /* assemble/mutation.py                                                       */
 /* ------------------------------------------------------------------------- */
 
+/* DenovoMCMC.llk_cache_threshold (assemble/mcmc.py:39, default 100; -1 disables) */
+static int64_t orc_llk_cache_threshold = 100;
+void orc_set_llk_cache_threshold(int64_t t) { orc_llk_cache_threshold = t; }
+
 typedef struct {
     const double *reads; /* f64[U,N,A] */
     int U, N, A;
@@ -680,8 +684,87 @@ typedef struct {
     int has_inbreeding; /* 0 => inbreeding is None (flat prior) */
     double inbreeding;
     double log_unique_haplotypes;
-    int64_t llk_evals; /* statistics: number of log_likelihood evaluations */
+    int64_t llk_evals; /* statistics: number of log_likelihood evaluations requested */
+    /* memo of log-likelihoods keyed by the ordered genotype: stands in for the reference's
+     * array-map cache (assemble/likelihood.py:152-305, assemble/arraymap.py; enabled iff
+     * ploidy * n_base * n_reads > llk_cache_threshold, assemble/mcmc.py:305-312).  Like the
+     * reference's cache it never changes a returned value (the llk is a deterministic function of
+     * the ordered genotype) and it is emptied when full. */
+    int use_cache;
+    int cache_bits;
+    uint64_t *cache_hash;
+    int8_t *cache_key;
+    double *cache_val;
+    int64_t cache_n;
+    int64_t cache_hits;
 } asm_ctx;
+
+static uint64_t geno_hash(const int8_t *g, size_t n)
+{
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < n; i++) {
+        h ^= (uint64_t)(uint8_t)g[i];
+        h *= 1099511628211ULL;
+    }
+    return h | 1ULL; /* 0 marks an empty slot */
+}
+
+static void asm_cache_init(asm_ctx *c, int enable)
+{
+    c->use_cache = enable;
+    c->cache_bits = 13;
+    c->cache_n = 0;
+    c->cache_hits = 0;
+    c->cache_hash = NULL;
+    c->cache_key = NULL;
+    c->cache_val = NULL;
+    if (enable) {
+        size_t cap = (size_t)1 << c->cache_bits;
+        c->cache_hash = (uint64_t *)calloc(cap, sizeof(uint64_t));
+        c->cache_key = (int8_t *)malloc(cap * (size_t)c->P * c->N);
+        c->cache_val = (double *)malloc(cap * sizeof(double));
+    }
+}
+
+static void asm_cache_free(asm_ctx *c)
+{
+    free(c->cache_hash);
+    free(c->cache_key);
+    free(c->cache_val);
+    c->cache_hash = NULL;
+    c->cache_key = NULL;
+    c->cache_val = NULL;
+}
+
+/* log_likelihood_cached (assemble/likelihood.py:195-235) on an explicit genotype */
+static double asm_llk_cached(asm_ctx *c, const int8_t *genotype)
+{
+    c->llk_evals++;
+    if (!c->use_cache)
+        return orc_log_likelihood(c->reads, c->U, c->N, c->A, genotype, c->P, c->counts);
+    const size_t gsz = (size_t)c->P * c->N;
+    const size_t cap = (size_t)1 << c->cache_bits;
+    const uint64_t h = geno_hash(genotype, gsz);
+    size_t s = (size_t)(h >> 17) & (cap - 1);
+    while (c->cache_hash[s]) {
+        if (c->cache_hash[s] == h && memcmp(c->cache_key + s * gsz, genotype, gsz) == 0) {
+            c->cache_hits++;
+            return c->cache_val[s];
+        }
+        s = (s + 1) & (cap - 1);
+    }
+    double v = orc_log_likelihood(c->reads, c->U, c->N, c->A, genotype, c->P, c->counts);
+    if ((size_t)c->cache_n * 2 >= cap) { /* empty the cache when (half) full */
+        memset(c->cache_hash, 0, cap * sizeof(uint64_t));
+        c->cache_n = 0;
+        s = (size_t)(h >> 17) & (cap - 1);
+    }
+    c->cache_hash[s] = h;
+    memcpy(c->cache_key + s * gsz, genotype, gsz);
+    c->cache_val[s] = v;
+    c->cache_n++;
+    return v;
+}
 
 static double np_minimum0(double x) /* np.minimum(0.0, x): NaN propagates */
 {
@@ -716,8 +799,7 @@ static double base_step(asm_ctx *c, orc_rng *rng, int8_t *genotype, double llk, 
         } else {
             n_options += 1;
             genotype[(size_t)h * N + j] = (int8_t)i;
-            double llk_i = orc_log_likelihood(c->reads, c->U, N, c->A, genotype, P, c->counts);
-            c->llk_evals++;
+            double llk_i = asm_llk_cached(c, genotype);
             llks[i] = llk_i;
             double llk_ratio = llk_i - llk;
             double lprior_ratio = 0.0;
@@ -993,9 +1075,18 @@ static double interval_step(asm_ctx *c, orc_rng *rng, int8_t *genotype, double l
         const int8_t *opt = options + (size_t)i * P * 2;
         for (int h = 0; h < P; h++)
             hap_idx[h] = opt[2 * h];
-        double llk_i = orc_log_likelihood_structural_change(c->reads, c->U, N, c->A, genotype, P,
-                                                            hap_idx, start, stop, c->counts);
-        c->llk_evals++;
+        double llk_i;
+        if (c->use_cache) { /* likelihood.py:239-305: key = the changed genotype */
+            int8_t *gnew = (int8_t *)malloc((size_t)P * N);
+            memcpy(gnew, genotype, (size_t)P * N);
+            orc_structural_change(gnew, P, N, hap_idx, start, stop);
+            llk_i = asm_llk_cached(c, gnew);
+            free(gnew);
+        } else {
+            llk_i = orc_log_likelihood_structural_change(c->reads, c->U, N, c->A, genotype, P, hap_idx,
+                                                         start, stop, c->counts);
+            c->llk_evals++;
+        }
         llks[i] = llk_i;
         double llk_ratio = llk_i - llk;
         double lprior_ratio = 0.0;
@@ -1109,6 +1200,7 @@ static void ctx_init(asm_ctx *c, const double *reads, int U, int N, int A, const
     c->inbreeding = inbreeding;
     c->log_unique_haplotypes = log_unique_haplotypes;
     c->llk_evals = 0;
+    asm_cache_init(c, 0);
 }
 
 double orc_mutation_base_step(orc_rng *rng, int8_t *genotype, int P, int N, const double *reads,
@@ -1189,6 +1281,9 @@ int orc_denovo_assembler(orc_rng *rng, const int8_t *genotype, int P, int N, con
     asm_ctx c;
     double log_unique_haplotypes = orc_log_unique_haplotypes(n_alleles, N); /* mcmc.py:294 */
     ctx_init(&c, reads, U, N, A, counts, P, inbreeding, log_unique_haplotypes);
+    /* assemble/mcmc.py:305-312 */
+    if (orc_llk_cache_threshold >= 0 && (int64_t)P * N * U > orc_llk_cache_threshold)
+        asm_cache_init(&c, 1);
     size_t gsz = (size_t)P * N;
     int8_t *genotypes = (int8_t *)malloc(gsz * (size_t)T + 1);
     double *llks = (double *)malloc(sizeof(double) * (size_t)T);
@@ -1256,6 +1351,7 @@ int orc_denovo_assembler(orc_rng *rng, const int8_t *genotype, int P, int N, con
         err = ORC_ERR_RNG_EXHAUSTED;
     if (out_llk_evals)
         *out_llk_evals = c.llk_evals;
+    asm_cache_free(&c);
     free(genotypes);
     free(llks);
     free(intervals);

@@ -147,6 +147,7 @@ def lib():
             C.c_double, C.c_int, _f64p, C.c_int, C.c_double, C.c_double, C.c_double, _f64p,
             C.c_int, _i8p, _f64p, _i64p,
         ]
+        L.orc_set_llk_cache_threshold.argtypes = [C.c_int64]
         L.orc_log_unique_haplotypes.restype = C.c_double
         L.orc_log_unique_haplotypes.argtypes = [_i8p, C.c_int]
         L.orc_homozygosity_probabilities.argtypes = [
@@ -281,6 +282,11 @@ class Rng:
         x = _i64(x)
         lib().orc_rng_shuffle_i64(self._h, _p(x, _i64p), len(x))
         return x
+
+
+def set_llk_cache_threshold(threshold):
+    """DenovoMCMC.llk_cache_threshold (assemble/mcmc.py:39): -1 disables the llk memo."""
+    lib().orc_set_llk_cache_threshold(int(threshold))
 
 
 def mt19937_words(seed, n):
