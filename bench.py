@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-items", type=int, default=0, help="items of the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-call-exact", action="store_true")
+    ap.add_argument("--exact-items", type=int, default=50000)
     return ap.parse_args()
 
 
@@ -83,7 +85,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_items = args.cpu_items or 6 * cores
+    n_items = args.cpu_items or 64 * cores
     vals = []
     for _ in range(args.warmup):
         cpu_oracle_rate(max(cores, n_items // 4), cores)
@@ -165,6 +167,53 @@ def algorithmic_flops(results, n_reads):
     n_het = results["n_het"].astype(np.float64)
     w = n_reads.astype(np.float64) * (PLOIDY * n_het + 2 * PLOIDY + 3)
     return float((results["llk_evals"].astype(np.float64) * w).sum())
+
+
+def call_exact_line(dev, args):
+    """Second half of BASELINE.json's metric: genotype likelihoods/s of call-exact on configs[2]
+    (hexaploid, 8 known haplotypes, all 1716 genotypes, 50k locus x sample pairs; the work of
+    exact.posterior_mode: mode + normaliser + support + allele frequencies).  Host buffers in,
+    results out (e2e) and kernel-only device time; CPU: the C oracle on a bounded sample."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from mchap_b200.api import CallBatch
+    from mchap_b200.synth import synth_haplotype_panel
+    from oracle import oracle as o
+
+    n, P, H, N = args.exact_items, 6, 8, 8
+    batch, panels, _ = synth_haplotype_panel(n, H, N, P, depth=DEPTH, seed=777)
+    reads = [batch.reads[batch.offsets[i]:batch.offsets[i + 1]] for i in range(n)]
+    counts = [batch.counts[batch.offsets[i]:batch.offsets[i + 1]] for i in range(n)]
+    cb = CallBatch(reads, list(panels), P, counts, [(0.1, None)] * n)
+    G = int(cb.n_genotypes[0])
+    dev.call_exact_mode(cb)
+    t0 = time.perf_counter()
+    reps = 3
+    kms = 0.0
+    for _ in range(reps):
+        dev.call_exact_mode(cb)
+        kms += dev.last_kernel_ms
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    n_cpu = min(n, 40 * cores)
+
+    def work(idx):
+        for i in idx:
+            o.posterior_mode(reads[i], P, panels[i], counts[i], (0.1, None), True, True, True)
+        return len(idx)
+
+    parts = [p for p in np.array_split(np.arange(n_cpu), cores) if len(p)]
+    t1 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        done = sum(ex.map(work, parts))
+    dcpu = time.perf_counter() - t1
+    return {
+        "metric": "genotype likelihoods/s (call-exact)", "unit": "genotypes/s",
+        "workload": "synthetic hexaploid call-exact: 8 known haplotypes/locus, all 1716 genotypes, %d locus x sample pairs" % n,
+        "value": n * G * reps / (kms * 1e-3), "e2e": n * G * reps / dt, "ms_per_pass": kms / reps,
+        "cpu_baseline": {"value": done * G / dcpu, "cores": cores, "kind": "port", "sample": "%d items" % n_cpu,
+                         "note": "the oracle's posterior_mode makes 2 enumeration passes per item like the reference"},
+    }
 
 
 def run_b200(args, rank, world):
@@ -303,10 +352,14 @@ def run_b200(args, rank, world):
         "hbm_peak_source": "MEASURED_PEAKS.json" if hbm_peak else "fallback",
     }
 
+    call_exact = None
+    if rank == 0 and not args.no_call_exact:
+        call_exact = call_exact_line(dev, args)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_items or 6 * cores
+        n_cpu = args.cpu_items or 200 * cores
         v, dt = cpu_oracle_rate(n_cpu, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d of the %d locus x sample items of the workload, %.1f s" % (n_cpu, LOCI * SAMPLES, dt)}
@@ -322,6 +375,7 @@ def run_b200(args, rank, world):
                        "l2": "each step reads a different batch and writes a 9.6 GB trace (> L2)",
                        "mean_unique_reads": float(np.mean([b.n_reads().mean() for b, _ in batches]))},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "call_exact": call_exact,
             "wall_ms_per_step": 1e3 * wall_max / K,
         }
         print(json.dumps(line), flush=True)

@@ -58,7 +58,7 @@ struct AsmArgs {
     int32_t smem_per_warp;      // bytes
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
-        o_nall, o_opt0, o_opt1, o_ivb, o_ivp;
+        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring;
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
@@ -232,15 +232,63 @@ __device__ __noinline__ double assemble_prior_rows(const uint64_t *rows, int P, 
     return ((LGAMMA_INT[P + 1] + scv[SC_LG_SUMDISP]) - scv[SC_LG_P_SUMDISP]) + acc;
 }
 
+// ---------------------------------------------------------------------------------------
+// The two numeric building blocks of the lanes-over-reads paths, kept out of line so that the
+// steady-state loop holds exactly one copy of each (the kernel is instruction-cache bound).
+// ---------------------------------------------------------------------------------------
+struct RowGeom {
+    int N, A, P, B;
+    uint32_t amask;
+    int pow2;
+    double invP;
+};
+
+// likelihood.py:48-60 for one haplotype key: row[r] = (prod_j Rt[j][allele_j][r]) / ploidy
+template <int CH>
+__device__ __noinline__ void compute_row(const double *Rt_lane, double *row_lane, uint64_t k, RowGeom g) {
+    constexpr int UPAD = CH * 32;
+    double out[CH];
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++) out[ch] = 1.0;
+    const double *base = Rt_lane;
+    const int pstride = g.A * UPAD;
+#pragma unroll 1
+    for (int j = 0; j < g.N; j++) {
+        const double *p = base + ((uint32_t)k & g.amask) * UPAD;
+        k >>= g.B;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) out[ch] *= p[ch * 32];
+        base += pstride;
+    }
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++) row_lane[ch * 32] = g.pow2 ? out[ch] * g.invP : out[ch] / (double)g.P;
+}
+
+// likelihood.py:45-68 from the cached rows of one state: sum over haplotypes in order, log,
+// * count, then the sum over reads as an xor butterfly (uniform result)
+template <int CH>
+__device__ __noinline__ double eval_rows(const double *q_lane, const double *cnt_lane, int P) {
+    constexpr int UPAD = CH * 32;
+    double acc = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++) {
+        double rp = 0.0;
+#pragma unroll 1
+        for (int h = 0; h < P; h++) rp += q_lane[h * UPAD + ch * 32];
+        acc += log(rp) * cnt_lane[ch * 32];
+    }
+    return warp_sum(acc);
+}
+
 template <int CH, bool PRIOR>
 struct AsmCtx {
     static constexpr int UPAD = CH * 32;
     const AsmArgs &a;
     unsigned char *sm;  // this warp's shared memory region
     int lane;
-    int N, A, P, B;
+    int N, A, P, B, U;
     uint32_t amask;
-    bool pow2, key32;
+    bool pow2;
     double invP;
     uint32_t slots;  // nibble t -> state slot (parallel tempering swaps exchange slots)
     WordStream ws;
@@ -281,83 +329,47 @@ struct AsmCtx {
             acc += p[i];
             p[i] = acc;
         }
-        double u = ws.next_double(lane);
+        double u = ws.next_double();
         return searchsorted_right(p, n, u);
     }
 
-    // products of one haplotype key over all positions, divided by the ploidy
-    // (likelihood.py:48-60): out[ch] belongs to read ch*32+lane
-    __device__ __forceinline__ void hap_products(uint64_t k, double (&out)[CH]) const {
-#pragma unroll
-        for (int ch = 0; ch < CH; ch++) out[ch] = 1.0;
-        const unsigned char *base = reinterpret_cast<const unsigned char *>(Rt() + lane);
-        const int astride = UPAD * 8;          // bytes between alleles
-        const int pstride = A * UPAD * 8;      // bytes between positions
-        if (key32) {
-            uint32_t kk = (uint32_t)k;
-#pragma unroll 4
-            for (int j = 0; j < N; j++) {
-                const double *p = reinterpret_cast<const double *>(base + (kk & amask) * astride);
-                kk >>= B;
-#pragma unroll
-                for (int ch = 0; ch < CH; ch++) out[ch] *= p[ch * 32];
-                base += pstride;
-            }
-        } else {
-#pragma unroll 2
-            for (int j = 0; j < N; j++) {
-                const double *p = reinterpret_cast<const double *>(base + ((uint32_t)k & amask) * astride);
-                k >>= B;
-#pragma unroll
-                for (int ch = 0; ch < CH; ch++) out[ch] *= p[ch * 32];
-                base += pstride;
-            }
-        }
-        if (pow2) {
-#pragma unroll
-            for (int ch = 0; ch < CH; ch++) out[ch] = out[ch] * invP;
-        } else {
-            const double dP = (double)P;
-#pragma unroll
-            for (int ch = 0; ch < CH; ch++) out[ch] = out[ch] / dP;
-        }
+    __device__ __forceinline__ RowGeom geom() const {
+        RowGeom g;
+        g.N = N;
+        g.A = A;
+        g.P = P;
+        g.B = B;
+        g.amask = amask;
+        g.pow2 = pow2 ? 1 : 0;
+        g.invP = invP;
+        return g;
     }
+    __device__ __forceinline__ double *qrow_lane(int s, int h) const { return q() + (size_t)(s * P + h) * UPAD + lane; }
+    // spare rows (two per warp) that hold the old rows of a proposal while it is installed
+    __device__ __forceinline__ double *spare_lane(int k) const { return q() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
 
-    // log-likelihood of state slot s from its cached product rows (likelihood.py:45-68 order:
-    // sum over h in order, log, * count, sum over reads)
+    // log-likelihood of state slot s from its cached product rows
     __device__ __forceinline__ double eval_llk(int s) {
-        double acc = 0.0;
-        const double *qq = q() + (size_t)(s * P) * UPAD + lane;
-        const double *cn = cnt() + lane;
-#pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
-            double rp = 0.0;
-#pragma unroll 4
-            for (int h = 0; h < P; h++) rp += qq[h * UPAD + ch * 32];
-            acc += log(rp) * cn[ch * 32];
-        }
         evals++;
-        return warp_sum(acc);
+        return eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
     }
 
-    // swap the product row of haplotype h of slot s with the vector held in registers: used to
-    // install a proposal before evaluating it and to restore the old row on rejection (each lane
-    // touches only its own column, so no warp synchronisation is needed)
-    __device__ __forceinline__ void swap_row(int s, int h, double (&v)[CH]) {
-        double *row = q() + (size_t)(s * P + h) * UPAD + lane;
+    // install the product row of key k as haplotype h of slot s, keeping the old row in spare[k_spare]
+    __device__ __forceinline__ void install_row(int s, int h, uint64_t k, int k_spare) {
+        double *row = qrow_lane(s, h), *sp = spare_lane(k_spare);
 #pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
-            const double old = row[ch * 32];
-            row[ch * 32] = v[ch];
-            v[ch] = old;
-        }
+        for (int ch = 0; ch < CH; ch++) sp[ch * 32] = row[ch * 32];
+        compute_row<CH>(Rt() + lane, row, k, geom());
     }
-
-    __device__ __forceinline__ void commit(int s, int h, uint64_t k, const double (&qa)[CH]) {
+    __device__ __forceinline__ void restore_row(int s, int h, int k_spare) {
+        double *row = qrow_lane(s, h), *sp = spare_lane(k_spare);
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) row[ch * 32] = sp[ch * 32];
+    }
+    // make key k haplotype h of slot s (row recomputed)
+    __device__ __forceinline__ void commit(int s, int h, uint64_t k) {
         keys(s)[h] = k;
-        double *row = q() + (size_t)(s * P + h) * UPAD + lane;
-#pragma unroll
-        for (int ch = 0; ch < CH; ch++) row[ch * 32] = qa[ch];
+        compute_row<CH>(Rt() + lane, qrow_lane(s, h), k, geom());
     }
 
     // prior of the haplotype keys of a slot with up to two haplotypes replaced
@@ -375,6 +387,33 @@ struct AsmCtx {
         return assemble_prior_rows(rows, P, sc(), lgdisp());
     }
 
+    // lane-local variant (different lanes evaluate different proposals): haplotype hA replaced by kA
+    __device__ __forceinline__ double prior_of_keys_lane(const uint64_t *ks, int hA, uint64_t kA) const {
+        const double *scv = sc();
+        const double *lgd = lgdisp();
+        const bool null_prior = scv[SC_INBREEDING] == 0.0;
+        const double lg_disp = scv[SC_LG_DISP];
+        double acc = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < P; i++) {
+            const uint64_t ki = (i == hA) ? kA : ks[i];
+            int cntv = 0;
+            bool first = true;
+#pragma unroll 1
+            for (int k = 0; k < P; k++) {
+                const uint64_t kk = (k == hA) ? kA : ks[k];
+                const bool eq = kk == ki;
+                cntv += eq;
+                first = first && !(eq && k < i);
+            }
+            const int dose = first ? cntv : 0;
+            if (null_prior) acc += LGAMMA_INT[dose + 1];
+            else if (dose > 0) acc += lgd[dose] - (LGAMMA_INT[dose + 1] + lg_disp);
+        }
+        if (null_prior) return (LGAMMA_INT[P + 1] - acc) - (double)P * scv[SC_LUH];
+        return ((LGAMMA_INT[P + 1] + scv[SC_LG_SUMDISP]) - scv[SC_LG_P_SUMDISP]) + acc;
+    }
+
     // prior of a label matrix (structural.py:546: dosage of the (inside, outside) label rows)
     __device__ __forceinline__ double prior_of_labels(uint64_t lin, uint64_t lout) const {
         uint64_t *rows = prow();
@@ -386,7 +425,10 @@ struct AsmCtx {
     }
 
     // ------------------------------------------------------------------ mutation.py:15-161
-    __device__ __forceinline__ void base_step(int s, int h, int j, int n_all, double temp, double &llk) {
+    // Serial form of one sub-step (any number of alleles).  u: the step's only uniform draw
+    // (random_choice), supplied by the caller.  Bi-allelic sub-steps normally take the
+    // lane-parallel path of mutation_compound_step instead.
+    __device__ __forceinline__ void base_step(int s, int h, int j, int n_all, double temp, double &llk, const double u) {
         uint64_t *ks = keys(s);
         const uint64_t kh = ks[h];
         const int shift = B * j;
@@ -398,46 +440,6 @@ struct AsmCtx {
         const double lhap = LOG_INT[__popc(__ballot_sync(MCHB_FULL, mine && myk == kh))];
         double lprior = 0.0;
         if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
-        double qn[CH];
-        if (n_all == 2 && cur < 2) {
-            // bi-allelic position: one proposal; identical arithmetic to the general path below
-            // (log(n_options) = log(1) = 0, exp(-inf) = 0 for the current allele).  The uniform
-            // is the only draw of the step, so drawing it first does not change the stream.
-            const double u = ws.next_double(lane);
-            const uint64_t kn = (kh & clr) | ((uint64_t)(cur ^ 1) << shift);
-            hap_products(kn, qn);
-            swap_row(s, h, qn);  // install the proposal, qn now holds the old row
-            const double llk_o = eval_llk(s);
-            double lprior_ratio = 0.0;
-            if (PRIOR) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - lprior;
-            const int copies_n = 1 + __popc(__ballot_sync(MCHB_FULL, mine && lane != h && myk == kn));
-            const double lprop = LOG_INT[copies_n] - lhap;
-            const double mh = ((llk_o - llk) + lprior_ratio) * temp + lprop;
-            const double la = np_minimum0(mh);
-            int choice;
-            if (la < -40.0 && u >= 1.1102230246251565e-16) {
-                // exp(la) < 2^-54: 1 - p rounds to 1 and p <= u, so the search returns `cur`
-                // whatever p is; skipping exp() leaves the outcome bit-identical
-                choice = cur;
-            } else {
-                const double p_o = exp(la - 0.0);
-                const double p_c = 1 - p_o;  // 1 - (0 + p_o)
-                const double cs0 = cur == 0 ? p_c : p_o;
-                const double cs1 = cs0 + (cur == 0 ? p_o : p_c);
-                choice = (cs1 <= u) ? 2 : ((cs0 <= u) ? 1 : 0);
-            }
-            if (choice >= 2) {
-                err = MCHB_ITEM_CHOICE_RANGE;
-                return;
-            }
-            if (choice != cur) {
-                ks[h] = kn;
-                llk = llk_o;
-            } else {
-                swap_row(s, h, qn);  // rejected: put the old row back
-            }
-            return;
-        }
         double *ol = oll(), *op = opr();
         int n_options = 0;
 #pragma unroll 1
@@ -448,10 +450,9 @@ struct AsmCtx {
             } else {
                 n_options++;
                 const uint64_t kn = (kh & clr) | ((uint64_t)i << shift);
-                hap_products(kn, qn);
-                swap_row(s, h, qn);
+                install_row(s, h, kn, 0);
                 const double llk_i = eval_llk(s);
-                swap_row(s, h, qn);
+                restore_row(s, h, 0);
                 ol[i] = llk_i;
                 const double llk_ratio = llk_i - llk;
                 double lprior_ratio = 0.0;
@@ -466,25 +467,34 @@ struct AsmCtx {
         double sum = 0.0;
 #pragma unroll 1
         for (int i = 0; i < n_all; i++) {
-            const double p = exp(op[i] - ln_opts);
+            const double p = dexp(op[i] - ln_opts);
             op[i] = p;
             sum += p;
         }
         op[cur] = 1 - sum;
-        const int choice = random_choice_inplace(op, n_all);
+        double cacc = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < n_all; i++) {
+            cacc += op[i];
+            op[i] = cacc;
+        }
+        const int choice = searchsorted_right(op, n_all, u);
         if (choice >= n_all) {
             err = MCHB_ITEM_CHOICE_RANGE;
             return;
         }
-        if (choice != cur) {
-            const uint64_t kn = (kh & clr) | ((uint64_t)choice << shift);
-            hap_products(kn, qn);
-            commit(s, h, kn, qn);
-        }
+        if (choice != cur) commit(s, h, (kh & clr) | ((uint64_t)choice << shift));
         llk = ol[choice];
     }
 
     // ------------------------------------------------------------------ mutation.py:165-246
+    // The P*N sub-steps are applied in shuffled order.  Each consumes exactly one uniform, so
+    // the draw of the i-th pending sub-step sits at a known offset of the word stream; and as
+    // long as no proposal is accepted they all start from the same state.  Lanes therefore
+    // evaluate up to 32 consecutive bi-allelic sub-steps AT ONCE (lane = sub-step, each lane
+    // walks the reads in read order like likelihood.py:45-68); the first accepting lane commits
+    // and the sub-steps behind it are re-evaluated from the new state.  A sub-step at a position
+    // with more than two alleles is a barrier handled by the serial base_step.
     __device__ __forceinline__ void mutation_compound_step(int s, double temp, double &llk) {
         const int n = P * N;
         uint16_t *pm = perm();
@@ -496,7 +506,7 @@ struct AsmCtx {
         __syncwarp();
 #pragma unroll 1
         for (int i = n - 1; i > 0; i--) {  // np.random.shuffle of the rows
-            int k = ws.randint(i + 1, lane);
+            int k = ws.randint(i + 1);
             uint16_t x = pm[i], y = pm[k];
             __syncwarp();
             pm[i] = y;
@@ -504,11 +514,106 @@ struct AsmCtx {
         }
         __syncwarp();
         const uint8_t *na = nall();
+        uint64_t *ks = keys(s);
+        const double *Rt0 = Rt();
+        const double *q0 = q() + (size_t)(s * P) * UPAD;
+        const double *cn = cnt();
+        int done = 0;
 #pragma unroll 1
-        for (int i = 0; i < n && !err; i++) {
-            int hj = pm[i];
-            int j = hj & 255;
-            base_step(s, hj >> 8, j, na[j], temp, llk);
+        while (done < n && !err) {
+            const int i = done + lane;
+            const bool active = i < n;
+            const int hj = pm[active ? i : done];
+            const int h = hj >> 8, j = hj & 255;
+            const uint64_t kh = ks[h];
+            const int shift = B * j;
+            const int cur = (int)((uint32_t)(kh >> shift) & amask);
+            const bool fast = na[j] == 2 && cur < 2;
+            const unsigned slow_mask = __ballot_sync(MCHB_FULL, active && !fast);
+            int limit = min(32, n - done);
+            if (slow_mask) limit = min(limit, __ffs(slow_mask) - 1);
+            if (limit == 0) {
+                // the next sub-step is not bi-allelic: serial path (uniform: all lanes agree)
+                const int hj0 = pm[done];
+                const double u0 = ws.next_double();
+                base_step(s, hj0 >> 8, hj0 & 255, na[hj0 & 255], temp, llk, u0);
+                done += 1;
+                continue;
+            }
+            const bool mine = lane < limit;
+            const uint64_t kn = (kh & ~((uint64_t)amask << shift)) | ((uint64_t)(cur ^ 1) << shift);
+            // ---- log-likelihood of my proposal: reads in order, haplotypes in order
+            double llk_o = 0.0;
+            {
+                const int astride = UPAD, pstride = A * UPAD;
+#pragma unroll 1
+                for (int r = 0; r < U; r++) {
+                    double prod = 1.0;
+                    const double *col = Rt0 + r;
+                    uint64_t kk = kn;
+#pragma unroll 2
+                    for (int jj = 0; jj < N; jj++) {
+                        prod *= col[((uint32_t)kk & amask) * astride];
+                        kk >>= B;
+                        col += pstride;
+                    }
+                    prod = pow2 ? prod * invP : prod / (double)P;
+                    double rp = 0.0;
+#pragma unroll 2
+                    for (int hh = 0; hh < P; hh++) {
+                        const double v = q0[hh * UPAD + r];
+                        rp += (hh == h) ? prod : v;
+                    }
+                    llk_o += log(rp) * cn[r];
+                }
+            }
+            // ---- my Metropolis-Hastings decision (mutation.py:84-155)
+            int copies_o = 0, copies_n = 1;
+#pragma unroll 1
+            for (int k = 0; k < P; k++) {
+                const uint64_t kk = ks[k];
+                copies_o += (kk == kh);
+                copies_n += (k != h && kk == kn);
+            }
+            double lprior_ratio = 0.0;
+            if (PRIOR) lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
+            const double mh = ((llk_o - llk) + lprior_ratio) * temp + (LOG_INT[copies_n] - LOG_INT[copies_o]);
+            const double la = np_minimum0(mh);
+            const double u = ws.double_at(2 * (mine ? lane : 0));
+            int choice;
+            if (la < -40.0 && u >= 1.1102230246251565e-16) {
+                choice = cur;  // exp(la) < 2^-54: see base_step
+            } else {
+                const double p_o = dexp(la - 0.0);
+                const double p_c = 1 - p_o;
+                const double cs0 = cur == 0 ? p_c : p_o;
+                const double cs1 = cs0 + (cur == 0 ? p_o : p_c);
+                choice = (cs1 <= u) ? 2 : ((cs0 <= u) ? 1 : 0);
+            }
+            const unsigned event = __ballot_sync(MCHB_FULL, mine && choice != cur);
+            if (event == 0) {
+                // every evaluated proposal was rejected
+                evals += limit;
+                ws.advance(2 * limit);
+                done += limit;
+                continue;
+            }
+            const int first = __ffs(event) - 1;
+            evals += first + 1;
+            ws.advance(2 * (first + 1));
+            done += first + 1;
+            const int ch1 = __shfl_sync(MCHB_FULL, choice, first);
+            if (ch1 >= 2) {
+                err = MCHB_ITEM_CHOICE_RANGE;
+                break;
+            }
+            // commit the first accepted proposal (uniform code: products across lanes = reads)
+            const int h1 = __shfl_sync(MCHB_FULL, h, first);
+            const uint64_t kn1 = __shfl_sync(MCHB_FULL, kn, first);
+            llk = __shfl_sync(MCHB_FULL, llk_o, first);
+            __syncwarp();
+            commit(s, h1, kn1);
+            __syncwarp();
         }
     }
 
@@ -527,7 +632,7 @@ struct AsmCtx {
         const int n_options = structural_options(lin, lout, P, step_type, o0, o1);
         __syncwarp();
         if (n_options == 0) return;  // no draw (structural.py:504-506)
-        const double u = ws.next_double(lane);  // the step's only draw (random_choice at the end)
+        const double u = ws.next_double();  // the step's only draw (random_choice at the end)
         const double log_proposal = LOG_INV_INT[n_options];
         double lprior = 0.0;
         if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
@@ -563,17 +668,11 @@ struct AsmCtx {
                 const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
                 const uint64_t lin_o = __shfl_sync(MCHB_FULL, lin_r, k);
                 const int n_return = __shfl_sync(MCHB_FULL, n_ret, k);
-                double qa[CH], qb[CH];
-                hap_products(k0n, qa);
-                swap_row(s, h0, qa);
-                if (step_type == 0) {
-                    const uint64_t k1n = (k0 & mask_in) | (k1 & ~mask_in);
-                    hap_products(k1n, qb);
-                    swap_row(s, h1, qb);
-                }
+                install_row(s, h0, k0n, 0);
+                if (step_type == 0) install_row(s, h1, (k0 & mask_in) | (k1 & ~mask_in), 1);
                 const double llk_i = eval_llk(s);
-                swap_row(s, h0, qa);
-                if (step_type == 0) swap_row(s, h1, qb);
+                restore_row(s, h0, 0);
+                if (step_type == 0) restore_row(s, h1, 1);
                 double lprior_ratio = 0.0;
                 if (PRIOR) lprior_ratio = prior_of_labels(lin_o, lout) - lprior;
                 const double lprop = LOG_INV_INT[n_return] - log_proposal;
@@ -607,7 +706,7 @@ struct AsmCtx {
         double sum = 0.0;
 #pragma unroll 1
         for (int i = 0; i <= n_options; i++) {
-            const double p = exp(op[i] - ln_opts);
+            const double p = dexp(op[i] - ln_opts);
             op[i] = p;
             sum += p;
         }
@@ -623,15 +722,8 @@ struct AsmCtx {
             const int h0 = o0[choice], h1 = o1[choice];
             const uint64_t k0 = ks[h0], k1 = ks[h1];
             const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
-            double qa[CH];
-            hap_products(k0n, qa);
-            if (step_type == 0) {
-                const uint64_t k1n = (k0 & mask_in) | (k1 & ~mask_in);
-                double qb[CH];
-                hap_products(k1n, qb);
-                commit(s, h1, k1n, qb);
-            }
-            commit(s, h0, k0n, qa);
+            if (step_type == 0) commit(s, h1, (k0 & mask_in) | (k1 & ~mask_in));
+            commit(s, h0, k0n);
             llk = ol[choice];
         }
     }
@@ -645,7 +737,7 @@ struct AsmCtx {
 #pragma unroll 1
         for (int sub = 0; sub < 3 && !err; sub++) {
             const double p_sub = sub == 0 ? a.p_recomb : (sub == 1 ? a.p_partial : a.p_dosage);
-            if (!(ws.next_double(lane) <= p_sub)) continue;
+            if (!(ws.next_double() <= p_sub)) continue;
             int n_int = 1;
             __syncwarp();
             if (sub < 2) {
@@ -664,7 +756,7 @@ struct AsmCtx {
                 for (int b = 0; b < n_breaks; b++) {
                     int m = __popcll(avail);
                     if (m == 0) break;
-                    int k = ws.randint(m, lane);  // np.random.choice(options)
+                    int k = ws.randint(m);  // np.random.choice(options)
                     uint64_t t = avail;
 #pragma unroll 1
                     for (int i = 0; i < k; i++) t &= t - 1;
@@ -683,7 +775,7 @@ struct AsmCtx {
                 __syncwarp();
 #pragma unroll 1
                 for (int i = n_int - 1; i > 0; i--) {  // np.random.permutation(np.arange(n))
-                    int k = ws.randint(i + 1, lane);
+                    int k = ws.randint(i + 1);
                     uint8_t x = vp[i], y = vp[k];
                     __syncwarp();
                     vp[i] = y;
@@ -717,9 +809,9 @@ struct AsmCtx {
         double post_i = llk_i + prior_i, post_j = llk_j + prior_j;
         double frac_1 = (post_j - post_i) * temp_i;
         double frac_2 = (post_i - post_j) * temp_j;
-        double acc = exp(frac_1 + frac_2);
+        double acc = dexp(frac_1 + frac_2);
         if (acc > 1.0) acc = 1.0;
-        double val = ws.next_double(lane);
+        double val = ws.next_double();
         if (acc >= val) {
             slots = (slots & ~((15u << (4 * t)) | (15u << (4 * (t - 1))))) | ((uint32_t)sj << (4 * t)) |
                     ((uint32_t)si << (4 * (t - 1)));
@@ -941,11 +1033,13 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
         const bool has_initial = a.initial != nullptr && itp->initial_off >= 0;
         c.A = A;
         c.P = P;
+        c.U = itp->n_reads > 0 ? itp->n_reads : 1;
         c.err = 0;
         c.evals = 0;
         c.invP = 1.0 / (double)P;
         c.pow2 = (P & (P - 1)) == 0;
-        c.ws.init(a.words + (size_t)a.item_stream[item_id] * a.stream_len, a.stream_len, lane);
+        c.ws.init(a.words + (size_t)a.item_stream[item_id] * a.stream_len, a.stream_len,
+                  reinterpret_cast<uint32_t *>(c.sm + a.o_ring), lane);
         int8_t *og = a.out_genotypes + itp->genotypes_off;
         double *ol = a.out_llks + itp->llks_off;
         const int step_sz = P * Nf;
@@ -955,7 +1049,6 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
         c.N = N;
         c.B = setup >> 16;
         c.amask = (1u << c.B) - 1u;
-        c.key32 = N * c.B <= 32;
 
         int status = 0;
         if (N == 0) {
@@ -1013,13 +1106,11 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
                 // ---- all temperatures start from the same state (mcmc.py:296-303)
                 c.slots = 0x76543210u;
                 {
-                    double qn[CH];
 #pragma unroll 1
                     for (int h = 0; h < P; h++) {
                         const uint64_t k = k0[h];
-                        c.hap_products(k, qn);
 #pragma unroll 1
-                        for (int t = 0; t < T; t++) c.commit(t, h, k, qn);
+                        for (int t = 0; t < T; t++) c.commit(t, h, k);
                     }
                     __syncwarp();
                     double llk0 = c.eval_llk(0);

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
     int *gs = reinterpret_cast<int *>(lgA + (size_t)a.hmax * (a.pmax + 2));  // [pmax] genotype
     int *ord = gs + a.pmax;                                         // [pmax] slot order
     int *ini = ord + a.pmax;                                        // [pmax] initial genotype
+    uint32_t *ring = reinterpret_cast<uint32_t *>(ini + a.pmax);    // [128] RNG word ring
 
     for (;;) {
         int w = 0;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
         const double inbreeding = it.inbreeding;
         const double dP = (double)P;
         WordStream ws;
-        ws.init(a.words + (size_t)a.item_stream[item_id] * a.stream_len, a.stream_len, lane);
+        ws.init(a.words + (size_t)a.item_stream[item_id] * a.stream_len, a.stream_len, ring, lane);
         long long evals = 0;
         int err = 0;
 
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                 for (int k = lane; k < P; k += 32) ord[k] = k;
                 __syncwarp();
                 for (int i = P - 1; i > 0; i--) {
-                    int k = ws.randint(i + 1, lane);
+                    int k = ws.randint(i + 1);
                     int x = ord[i], y = ord[k];
                     __syncwarp();
                     ord[i] = y;
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                     }
                     __syncwarp();
                     // ---- random_choice (jitutils.py:77-92): cumsum, searchsorted right
-                    const double u = ws.next_double(lane);
+                    const double u = ws.next_double();
                     double carry = 0.0;
                     int choice = 0;
                     for (int a0 = 0; a0 < H; a0 += 32) {

@@ -29,53 +29,78 @@ __constant__ double LGAMMA_INT[MCHB_TABLE_N];
 __constant__ float LOGF_INT[MCHB_TABLE_N];
 
 // ---------------------------------------------------------------------------------------
-// Word source: numba's MT19937 output stream, pre-generated in global memory (tempered
-// words).  Each lane keeps one word of the current 32-word block and of the next block in
-// registers; next_u32() is a warp shuffle.  Cursor is warp-uniform.
+// Word source: numba's MT19937 output stream, pre-generated in global memory (tempered words).
+// A 128-word ring in shared memory (4 blocks of 32) always holds the block under the cursor and the
+// next two, so that the sequential consumer (next_u32: one broadcast LDS) and lane-parallel
+// consumers (word_at(off), off < 64: lane i decodes the draw of the i-th pending sub-step) read
+// without touching global memory.  The cursor is warp-uniform.
 // Reference semantics: numba/cpython/randomimpl.py get_next_int32 109-132.
 // ---------------------------------------------------------------------------------------
 struct WordStream {
     const uint32_t *base;
+    uint32_t *ring;   // shared memory, 128 words
     int len;          // words available (< 2^31; reads beyond it return 0 and flag exhaustion at the end)
     int cur;          // words consumed so far (uniform)
-    uint32_t w_cur;   // lane's word of block cur/32
-    uint32_t w_next;  // lane's word of block cur/32 + 1
+    int lane;
 
-    __device__ __forceinline__ uint32_t load_block(int blk, int lane) const {
+    __device__ __forceinline__ uint32_t load_block(int blk) const {
         const int i = blk * 32 + lane;
         return (i < len) ? __ldg(base + i) : 0u;
     }
-    __device__ __forceinline__ void init(const uint32_t *b, int64_t n, int lane) {
+    __device__ __forceinline__ void init(const uint32_t *b, int64_t n, uint32_t *ring_smem, int lane_id) {
         base = b;
         len = (int)n;
+        ring = ring_smem;
+        lane = lane_id;
         cur = 0;
-        w_cur = load_block(0, lane);
-        w_next = load_block(1, lane);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 3; k++) ring[k * 32 + lane] = load_block(k);
+        __syncwarp();
     }
     __device__ __forceinline__ bool exhausted() const { return cur > len; }
-    __device__ __forceinline__ uint32_t next_u32(int lane) {
-        const int k = cur & 31;
-        const uint32_t w = __shfl_sync(MCHB_FULL, w_cur, k);
+    // the cursor just entered block cur/32: fetch block cur/32 + 2 into the slot of block cur/32 - 2
+    __device__ __forceinline__ void refill() {
+        const int blk = (cur >> 5) + 2;
+        __syncwarp();
+        ring[(blk & 3) * 32 + lane] = load_block(blk);
+        __syncwarp();
+    }
+    __device__ __forceinline__ uint32_t next_u32() {
+        const uint32_t w = ring[cur & 127];
         cur++;
-        if (k == 31) {
-            w_cur = w_next;
-            w_next = load_block((cur >> 5) + 1, lane);
-        }
+        if ((cur & 31) == 0) refill();
         return w;
     }
-    // randomimpl.py:134-147 get_next_double
-    __device__ __forceinline__ double next_double(int lane) {
-        uint32_t a = next_u32(lane) >> 5;
-        uint32_t b = next_u32(lane) >> 6;
+    // word at cursor + off without consuming it (0 <= off < 64)
+    __device__ __forceinline__ uint32_t word_at(int off) const { return ring[(cur + off) & 127]; }
+    // consume m words at once (m <= 64)
+    __device__ __forceinline__ void advance(int m) {
+        const int target = cur + m;
+        while ((cur >> 5) < (target >> 5)) {
+            cur = ((cur >> 5) + 1) << 5;
+            refill();
+        }
+        cur = target;
+    }
+    __device__ __forceinline__ static double to_double(uint32_t w0, uint32_t w1) {
+        const uint32_t a = w0 >> 5, b = w1 >> 6;  // randomimpl.py:134-147 get_next_double
         return ((double)b + (double)a * 67108864.0) / 9007199254740992.0;
     }
+    __device__ __forceinline__ double next_double() {
+        const uint32_t w0 = next_u32();
+        const uint32_t w1 = next_u32();
+        return to_double(w0, w1);
+    }
+    // the double that the (off/2)-th next call of next_double() would return (off even, < 63)
+    __device__ __forceinline__ double double_at(int off) const { return to_double(word_at(off), word_at(off + 1)); }
     // randomimpl.py:454-520 _randrange_impl (state "np", n <= 2^31 here); n == 1 draws nothing.
     // Past the end of the stream the words are 0, which ends the rejection loop.
-    __device__ __forceinline__ int randint(int n, int lane) {
+    __device__ __forceinline__ int randint(int n) {
         if (n == 1) return 0;
         const uint32_t mask = 0xffffffffu >> __clz(n - 1);
         for (;;) {
-            uint32_t r = next_u32(lane) & mask;
+            uint32_t r = next_u32() & mask;
             if ((int)r < n) return (int)r;
         }
     }

@@ -358,7 +358,7 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     };
     take((size_t)g.nmax * g.amax * upad * 8, 16);                      // Rt at 0
     args.o_cnt = take(upad * 8, 8);
-    args.o_q = take((size_t)g.tmax * g.pmax * upad * 8, 8);
+    args.o_q = take(((size_t)g.tmax * g.pmax + 2) * upad * 8, 8);  // + 2 spare rows
     args.o_dist = take((size_t)g.nmax * g.amax * 8, 8);
     args.o_oll = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_opr = take((size_t)(g.maxopt + 1) * 8, 8);
@@ -375,6 +375,7 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_opt1 = take((size_t)g.maxopt + 1, 1);
     args.o_ivb = take((size_t)g.nmax + 2, 1);
     args.o_ivp = take((size_t)g.nmax + 2, 1);
+    args.o_ring = take(128 * 4, 4);
     return (off + 15) & ~(size_t)15;
 }
 
@@ -945,7 +946,7 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
         words_needed = std::max(words_needed, (int64_t)pp.chains * pp.steps * (4 * (int64_t)it.ploidy + 8) + 64);
     }
     const size_t per_warp =
-        (((size_t)g.umax * g.hmax + g.umax + 2 * (size_t)g.hmax + (size_t)g.hmax * (g.pmax + 2)) * 8 + 3 * (size_t)g.pmax * 4 + 15) &
+        (((size_t)g.umax * g.hmax + g.umax + 2 * (size_t)g.hmax + (size_t)g.hmax * (g.pmax + 2)) * 8 + 3 * (size_t)g.pmax * 4 + 512 + 15) &
         ~(size_t)15;
     int warps_per_cta = 4;
     while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
