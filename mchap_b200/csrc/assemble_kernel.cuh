@@ -27,7 +27,7 @@
 
 // resident CTAs per SM the register allocation is tuned for (4 warps per CTA)
 #ifndef MCHB_ASM_MINBLOCKS
-#define MCHB_ASM_MINBLOCKS 4
+#define MCHB_ASM_MINBLOCKS 5
 #endif
 
 namespace mchb {
@@ -58,11 +58,15 @@ struct AsmArgs {
     int32_t smem_per_warp;      // bytes
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
-        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring;
+        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32;
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
-enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC_COUNT };
+enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC_MARGIN, SC_COUNT };
+
+// more needy sub-steps than this in one window: evaluate the window with the lane-parallel exact
+// loop instead of one exact evaluation per needy sub-step
+#define MCHB_EXACT_SERIAL_MAX 8
 
 // nibble helpers for packed small-integer vectors (labels, SNP genotypes), P <= 16
 __device__ __forceinline__ int nib(uint64_t v, int i) { return (int)((v >> (4 * i)) & 15u); }
@@ -245,7 +249,8 @@ struct RowGeom {
 
 // likelihood.py:48-60 for one haplotype key: row[r] = (prod_j Rt[j][allele_j][r]) / ploidy
 template <int CH>
-__device__ __noinline__ void compute_row(const double *Rt_lane, double *row_lane, uint64_t k, RowGeom g) {
+__device__ __noinline__ void compute_row(const double *Rt_lane, double *row_lane, float *row32_lane, uint64_t k,
+                                         RowGeom g) {
     constexpr int UPAD = CH * 32;
     double out[CH];
 #pragma unroll
@@ -261,7 +266,11 @@ __device__ __noinline__ void compute_row(const double *Rt_lane, double *row_lane
         base += pstride;
     }
 #pragma unroll
-    for (int ch = 0; ch < CH; ch++) row_lane[ch * 32] = g.pow2 ? out[ch] * g.invP : out[ch] / (double)g.P;
+    for (int ch = 0; ch < CH; ch++) {
+        const double v = g.pow2 ? out[ch] * g.invP : out[ch] / (double)g.P;
+        row_lane[ch * 32] = v;
+        row32_lane[ch * 32] = (float)v;  // shadow copy for the float32 screening pass
+    }
 }
 
 // likelihood.py:45-68 from the cached rows of one state: sum over haplotypes in order, log,
@@ -348,6 +357,12 @@ struct AsmCtx {
     // spare rows (two per warp) that hold the old rows of a proposal while it is installed
     __device__ __forceinline__ double *spare_lane(int k) const { return q() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
 
+    __device__ __forceinline__ float *q32() const { return reinterpret_cast<float *>(sm + a.o_q32); }
+    __device__ __forceinline__ float *rat() const { return reinterpret_cast<float *>(sm + a.o_rat); }
+    __device__ __forceinline__ float *c32() const { return reinterpret_cast<float *>(sm + a.o_c32); }
+    __device__ __forceinline__ float *qrow32_lane(int s, int h) const { return q32() + (size_t)(s * P + h) * UPAD + lane; }
+    __device__ __forceinline__ float *spare32_lane(int k) const { return q32() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
+
     // log-likelihood of state slot s from its cached product rows
     __device__ __forceinline__ double eval_llk(int s) {
         evals++;
@@ -357,19 +372,27 @@ struct AsmCtx {
     // install the product row of key k as haplotype h of slot s, keeping the old row in spare[k_spare]
     __device__ __forceinline__ void install_row(int s, int h, uint64_t k, int k_spare) {
         double *row = qrow_lane(s, h), *sp = spare_lane(k_spare);
+        float *row32 = qrow32_lane(s, h), *sp32 = spare32_lane(k_spare);
 #pragma unroll
-        for (int ch = 0; ch < CH; ch++) sp[ch * 32] = row[ch * 32];
-        compute_row<CH>(Rt() + lane, row, k, geom());
+        for (int ch = 0; ch < CH; ch++) {
+            sp[ch * 32] = row[ch * 32];
+            sp32[ch * 32] = row32[ch * 32];
+        }
+        compute_row<CH>(Rt() + lane, row, row32, k, geom());
     }
     __device__ __forceinline__ void restore_row(int s, int h, int k_spare) {
         double *row = qrow_lane(s, h), *sp = spare_lane(k_spare);
+        float *row32 = qrow32_lane(s, h), *sp32 = spare32_lane(k_spare);
 #pragma unroll
-        for (int ch = 0; ch < CH; ch++) row[ch * 32] = sp[ch * 32];
+        for (int ch = 0; ch < CH; ch++) {
+            row[ch * 32] = sp[ch * 32];
+            row32[ch * 32] = sp32[ch * 32];
+        }
     }
     // make key k haplotype h of slot s (row recomputed)
     __device__ __forceinline__ void commit(int s, int h, uint64_t k) {
         keys(s)[h] = k;
-        compute_row<CH>(Rt() + lane, qrow_lane(s, h), k, geom());
+        compute_row<CH>(Rt() + lane, qrow_lane(s, h), qrow32_lane(s, h), k, geom());
     }
 
     // prior of the haplotype keys of a slot with up to two haplotypes replaced
@@ -542,7 +565,100 @@ struct AsmCtx {
             }
             const bool mine = lane < limit;
             const uint64_t kn = (kh & ~((uint64_t)amask << shift)) | ((uint64_t)(cur ^ 1) << shift);
-            // ---- log-likelihood of my proposal: reads in order, haplotypes in order
+            // ---- the parts of my Metropolis-Hastings ratio that do not need the likelihood
+            int copies_o = 0, copies_n = 1;
+#pragma unroll 1
+            for (int k = 0; k < P; k++) {
+                const uint64_t kk = ks[k];
+                copies_o += (kk == kh);
+                copies_n += (k != h && kk == kn);
+            }
+            double lprior_ratio = 0.0;
+            if (PRIOR) lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
+            const double lprop = LOG_INT[copies_n] - LOG_INT[copies_o];
+            const double u = ws.double_at(2 * (mine ? lane : 0));
+            // ---- tier 1: float32 screening.  The proposal's row is the cached row of haplotype h
+            // times R[j][new] / R[j][old] (exact in real arithmetic); with float32 roundings and
+            // __logf the log-likelihood is off by < 5e-5 per read observation, far inside `margin`.
+            // The exact step accepts only if exp(min(0, mh)) reaches t = u (current allele 1) or
+            // t = 1 - u (current allele 0) — see the cumulative sums in base_step — so a sub-step
+            // whose screened mh is below log(t) - margin is certainly rejected and needs no exact
+            // evaluation; everything else ("needy") is decided exactly below.
+            double a32 = 0.0;
+            bool sane = true;
+            {
+                const float *qs = q32() + (size_t)(s * P) * UPAD;
+                const float *rt = rat() + (size_t)(j * 2 + (cur & 1)) * UPAD;
+                const float *cw = c32();
+#pragma unroll 2
+                for (int r = 0; r < U; r++) {
+                    const float qh = qs[h * UPAD + r] * rt[r];
+                    float rp = 0.f;
+#pragma unroll 2
+                    for (int hh = 0; hh < P; hh++) {
+                        const float v = qs[hh * UPAD + r];
+                        rp += (hh == h) ? qh : v;
+                    }
+                    sane = sane && (rp > 1e-30f) && (rp < 1e30f);
+                    a32 += (double)(__logf(rp) * cw[r]);
+                }
+            }
+            const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
+            const double t_acc = (cur == 1) ? u : 1.0 - u;
+            const bool hopeless = sane && (mh32 < (double)__logf((float)t_acc) - sc()[SC_MARGIN]) &&
+                                  (u < 0.99999999999999911182);  // 1 - 2^-50: keep clear of the cs1 <= u corner
+            const unsigned needy = __ballot_sync(MCHB_FULL, mine && !hopeless);
+            if (__popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
+                // ---- tier 2a: exact decisions for the needy sub-steps, in order (uniform code)
+                int completed = limit;
+                unsigned m = needy;
+#pragma unroll 1
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int hl = __shfl_sync(MCHB_FULL, h, l);
+                    const int curl = __shfl_sync(MCHB_FULL, cur, l);
+                    const uint64_t knl = __shfl_sync(MCHB_FULL, kn, l);
+                    const double ul = __shfl_sync(MCHB_FULL, u, l);
+                    const double lrest = __shfl_sync(MCHB_FULL, lprior_ratio, l);
+                    const double lpropl = __shfl_sync(MCHB_FULL, lprop, l);
+                    install_row(s, hl, knl, 0);
+                    const double llk_x = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
+                    const double mh = ((llk_x - llk) + lrest) * temp + lpropl;
+                    const double la = np_minimum0(mh);
+                    int choice;
+                    if (la < -40.0 && ul >= 1.1102230246251565e-16) {
+                        choice = curl;
+                    } else {
+                        const double p_o = dexp(la - 0.0);
+                        const double p_c = 1 - p_o;  // 1 - (0 + p_o)
+                        const double cs0 = curl == 0 ? p_c : p_o;
+                        const double cs1 = cs0 + (curl == 0 ? p_o : p_c);
+                        choice = (cs1 <= ul) ? 2 : ((cs0 <= ul) ? 1 : 0);
+                    }
+                    if (choice == curl) {
+                        restore_row(s, hl, 0);
+                        continue;
+                    }
+                    completed = l + 1;
+                    if (choice >= 2) {
+                        restore_row(s, hl, 0);
+                        err = MCHB_ITEM_CHOICE_RANGE;
+                    } else {
+                        __syncwarp();
+                        ks[hl] = knl;  // the row is already installed
+                        llk = llk_x;
+                        __syncwarp();
+                    }
+                    break;
+                }
+                evals += completed;
+                ws.advance(2 * completed);
+                done += completed;
+                continue;
+            }
+            // ---- tier 2b: many needy sub-steps: exact log-likelihood of every proposal of the
+            // window, lane-parallel (reads in order, haplotypes in order)
             double llk_o = 0.0;
             {
                 const int astride = UPAD, pstride = A * UPAD;
@@ -567,19 +683,8 @@ struct AsmCtx {
                     llk_o += log(rp) * cn[r];
                 }
             }
-            // ---- my Metropolis-Hastings decision (mutation.py:84-155)
-            int copies_o = 0, copies_n = 1;
-#pragma unroll 1
-            for (int k = 0; k < P; k++) {
-                const uint64_t kk = ks[k];
-                copies_o += (kk == kh);
-                copies_n += (k != h && kk == kn);
-            }
-            double lprior_ratio = 0.0;
-            if (PRIOR) lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
-            const double mh = ((llk_o - llk) + lprior_ratio) * temp + (LOG_INT[copies_n] - LOG_INT[copies_o]);
+            const double mh = ((llk_o - llk) + lprior_ratio) * temp + lprop;
             const double la = np_minimum0(mh);
-            const double u = ws.double_at(2 * (mine ? lane : 0));
             int choice;
             if (la < -40.0 && u >= 1.1102230246251565e-16) {
                 choice = cur;  // exp(la) < 2^-54: see base_step
@@ -992,6 +1097,26 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
         if (isnan(v)) Rt[i] = 1.0;
     }
     __syncwarp();
+    // ---- float32 screening tables: allele ratios of bi-allelic flips, counts, safety margin
+    {
+        float *rat = reinterpret_cast<float *>(sm + a.o_rat);
+        float *c32 = reinterpret_cast<float *>(sm + a.o_c32);
+        for (int i = lane; i < N * UPAD; i += 32) {
+            const int k = i / UPAD, r = i - k * UPAD;
+            const double r0 = Rt[(k * A + 0) * UPAD + r];
+            const double r1 = A > 1 ? Rt[(k * A + 1) * UPAD + r] : r0;
+            rat[(k * 2 + 0) * UPAD + r] = (float)(r1 / r0);  // current allele 0 -> 1
+            rat[(k * 2 + 1) * UPAD + r] = (float)(r0 / r1);  // current allele 1 -> 0
+        }
+        double csum = 0.0;
+        for (int r = lane; r < UPAD; r += 32) {
+            c32[r] = (float)cnt[r];
+            csum += cnt[r];
+        }
+        csum = warp_sum(csum);
+        if (lane == 0) scv[SC_MARGIN] = 2.0 + 1e-4 * csum;
+        __syncwarp();
+    }
     // ---- per-item prior constants
     {
         float s = 0.0f;  // mcmc.py:294: float32 arithmetic in numba (int8 array)

@@ -376,6 +376,9 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_ivb = take((size_t)g.nmax + 2, 1);
     args.o_ivp = take((size_t)g.nmax + 2, 1);
     args.o_ring = take(128 * 4, 4);
+    args.o_q32 = take(((size_t)g.tmax * g.pmax + 2) * upad * 4, 4);
+    args.o_rat = take((size_t)g.nmax * 2 * upad * 4, 4);
+    args.o_c32 = take(upad * 4, 4);
     return (off + 15) & ~(size_t)15;
 }
 
