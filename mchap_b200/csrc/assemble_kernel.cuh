@@ -749,6 +749,67 @@ struct AsmCtx {
             my_lin = nib_set(lin, h0, nib(lin, h1));
             if (step_type == 0) my_lin = nib_set(my_lin, h1, nib(lin, h0));
         }
+        // ---- float32 screening (all variable positions bi-allelic, <= 32 options): the step
+        // stays put unless sum_i exp(min(0, mh_i)) / n exceeds u; with every screened mh_i below
+        // log(u) - margin that sum is below u / e^2, so "stay" is certain and no exact
+        // log-likelihood is needed (same error budget as in mutation_compound_step).
+        if (B == 1 && n_options <= 32 && u > 0.0 && u < 0.99999999999999911182) {
+            const int n_ret = structural_options(my_lin, lout, P, step_type, nullptr, nullptr);
+            const double bound = (double)__logf((float)u) - sc()[SC_MARGIN];
+            const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
+            const float *rt = rat() + lane;
+            const float *cw = c32() + lane;
+            bool certain = true;
+#pragma unroll 1
+            for (int k = 0; k < n_options && certain; k++) {
+                const int h0 = o0[k], h1 = o1[k];
+                const uint64_t k0 = ks[h0], k1 = ks[h1];
+                float ra[CH], rb[CH];
+#pragma unroll
+                for (int ch = 0; ch < CH; ch++) {
+                    ra[ch] = qs[h0 * UPAD + ch * 32];
+                    rb[ch] = qs[h1 * UPAD + ch * 32];
+                }
+                uint64_t d = (k0 ^ k1) & mask_in;  // positions where the swapped / copied segment differs
+#pragma unroll 1
+                while (d) {
+                    const int jp = __ffsll((long long)d) - 1;
+                    d &= d - 1;
+                    const int c0 = (int)((k0 >> jp) & 1ull);
+#pragma unroll
+                    for (int ch = 0; ch < CH; ch++) {
+                        ra[ch] *= rt[(jp * 2 + c0) * UPAD + ch * 32];       // h0 takes h1's allele
+                        rb[ch] *= rt[(jp * 2 + (c0 ^ 1)) * UPAD + ch * 32]; // h1 takes h0's allele (recombination)
+                    }
+                }
+                float acc = 0.f;
+                bool ok = true;
+#pragma unroll
+                for (int ch = 0; ch < CH; ch++) {
+                    float rp = 0.f;
+#pragma unroll 1
+                    for (int hh = 0; hh < P; hh++) {
+                        float v = qs[hh * UPAD + ch * 32];
+                        v = (hh == h0) ? ra[ch] : v;
+                        v = (step_type == 0 && hh == h1) ? rb[ch] : v;
+                        rp += v;
+                    }
+                    ok = ok && (rp > 1e-30f) && (rp < 1e30f);
+                    acc += __logf(rp) * cw[ch * 32];
+                }
+                const double a32 = warp_sum((double)acc);
+                const bool sane = __all_sync(MCHB_FULL, ok);
+                double lprior_ratio = 0.0;
+                if (PRIOR) lprior_ratio = prior_of_labels(__shfl_sync(MCHB_FULL, my_lin, k), lout) - lprior;
+                const double lprop = LOG_INV_INT[__shfl_sync(MCHB_FULL, n_ret, k)] - log_proposal;
+                const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
+                certain = sane && (mh32 < bound);
+            }
+            if (certain) {
+                evals += n_options;
+                return;
+            }
+        }
         int my_return = 1;
         double my_la = -INFINITY;
 #pragma unroll 1
@@ -1114,7 +1175,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
             csum += cnt[r];
         }
         csum = warp_sum(csum);
-        if (lane == 0) scv[SC_MARGIN] = 2.0 + 1e-4 * csum;
+        if (lane == 0) scv[SC_MARGIN] = 2.0 + 2e-4 * csum;
         __syncwarp();
     }
     // ---- per-item prior constants
