@@ -58,7 +58,7 @@ struct AsmArgs {
     int32_t smem_per_warp;      // bytes
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
-        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32;
+        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs;
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
@@ -363,6 +363,23 @@ struct AsmCtx {
     __device__ __forceinline__ float *qrow32_lane(int s, int h) const { return q32() + (size_t)(s * P + h) * UPAD + lane; }
     __device__ __forceinline__ float *spare32_lane(int k) const { return q32() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
 
+    // float32 per-read probability of the current state of slot s (sum of its shadow rows);
+    // refreshed whenever a row of the slot changes for good
+    __device__ __forceinline__ float *rpc_lane(int s) const { return reinterpret_cast<float *>(sm + a.o_rpc) + (size_t)s * UPAD + lane; }
+    __device__ __forceinline__ void refresh_rpc(int s) {
+        const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
+        float *dst = rpc_lane(s);
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+            float rp = 0.f;
+#pragma unroll 1
+            for (int hh = 0; hh < P; hh++) rp += qs[hh * UPAD + ch * 32];
+            dst[ch * 32] = rp;
+        }
+        __syncwarp();
+    }
+
     // log-likelihood of state slot s from its cached product rows
     __device__ __forceinline__ double eval_llk(int s) {
         evals++;
@@ -393,6 +410,7 @@ struct AsmCtx {
     __device__ __forceinline__ void commit(int s, int h, uint64_t k) {
         keys(s)[h] = k;
         compute_row<CH>(Rt() + lane, qrow_lane(s, h), qrow32_lane(s, h), k, geom());
+        refresh_rpc(s);
     }
 
     // prior of the haplotype keys of a slot with up to two haplotypes replaced
@@ -587,19 +605,19 @@ struct AsmCtx {
             double a32 = 0.0;
             bool sane = true;
             {
-                const float *qs = q32() + (size_t)(s * P) * UPAD;
+                // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.  The
+                // subtraction hidden in it can lose relative accuracy when the proposal removes almost
+                // all of a read's probability, so reads with rp_new < 1e-4 rp_cur make the sub-step
+                // needy (exact path); above that the relative error stays below 1e-3 (in the margin).
+                const float *qh = q32() + (size_t)(s * P + h) * UPAD;
+                const float *rc = reinterpret_cast<const float *>(sm + a.o_rpc) + (size_t)s * UPAD;
                 const float *rt = rat() + (size_t)(j * 2 + (cur & 1)) * UPAD;
                 const float *cw = c32();
-#pragma unroll 2
+#pragma unroll 4
                 for (int r = 0; r < U; r++) {
-                    const float qh = qs[h * UPAD + r] * rt[r];
-                    float rp = 0.f;
-#pragma unroll 2
-                    for (int hh = 0; hh < P; hh++) {
-                        const float v = qs[hh * UPAD + r];
-                        rp += (hh == h) ? qh : v;
-                    }
-                    sane = sane && (rp > 1e-30f) && (rp < 1e30f);
+                    const float rc_r = rc[r];
+                    const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
+                    sane = sane && (rp > 1e-4f * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
                     a32 += (double)(__logf(rp) * cw[r]);
                 }
             }
@@ -648,7 +666,7 @@ struct AsmCtx {
                         __syncwarp();
                         ks[hl] = knl;  // the row is already installed
                         llk = llk_x;
-                        __syncwarp();
+                        refresh_rpc(s);
                     }
                     break;
                 }
@@ -907,10 +925,9 @@ struct AsmCtx {
             int n_int = 1;
             __syncwarp();
             if (sub < 2) {
-                double *op = opr();
-#pragma unroll 1
-                for (int i = 0; i < blen; i++) op[i] = brow[i];
-                const int n_breaks = random_choice_inplace(op, blen);
+                // random_choice(break_dist): cumulative sums prepared once per item (bcs)
+                const double ub = ws.next_double();
+                const int n_breaks = searchsorted_right(reinterpret_cast<const double *>(sm + a.o_bcs), blen, ub);
                 if (n_breaks >= N) {
                     err = MCHB_ITEM_BREAKS;
                     return;
@@ -1175,7 +1192,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
             csum += cnt[r];
         }
         csum = warp_sum(csum);
-        if (lane == 0) scv[SC_MARGIN] = 2.0 + 2e-4 * csum;
+        if (lane == 0) scv[SC_MARGIN] = 2.0 + 2e-3 * csum;
         __syncwarp();
     }
     // ---- per-item prior constants
@@ -1257,6 +1274,18 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
             const int blen = a.break_len[brow_i];
             const double *temps = a.temperatures + itp->temps_off;
             double *lt = c.llk_t();
+            {
+                // np.cumsum(break_dist), sequential like numba (jitutils.py:92)
+                double *bcs = reinterpret_cast<double *>(c.sm + a.o_bcs);
+                double acc = 0.0;
+                __syncwarp();
+#pragma unroll 1
+                for (int i = 0; i < blen; i++) {
+                    acc += brow[i];
+                    bcs[i] = acc;
+                }
+                __syncwarp();
+            }
 
 #pragma unroll 1
             for (int chain = 0; chain < a.chains && !c.err; chain++) {

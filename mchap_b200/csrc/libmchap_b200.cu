@@ -379,6 +379,8 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_q32 = take(((size_t)g.tmax * g.pmax + 2) * upad * 4, 4);
     args.o_rat = take((size_t)g.nmax * 2 * upad * 4, 4);
     args.o_c32 = take(upad * 4, 4);
+    args.o_rpc = take((size_t)g.tmax * upad * 4, 4);
+    args.o_bcs = take((size_t)(g.maxopt + 1) * 8, 8);
     return (off + 15) & ~(size_t)15;
 }
 
