@@ -368,3 +368,39 @@ def test_calling_mcmc_batch_vs_oracle(dev, oracle, ploidy, n_haps, step_type, pr
         np.testing.assert_array_equal(traces[i].genotypes, ref["genotypes"], err_msg="item %d" % i)
         close(traces[i].llks, ref["llks"])
         assert results["rng_words"][i] == ref["words"]
+
+
+# ----------------------------------------------------------------------------- screening stress
+@pytest.mark.parametrize("ploidy,n_pos,depth,error_rate,inbreeding,temps,seed", [
+    (4, 8, 5, 0.0024, None, (1.0,), 1),       # very low depth: many plausible proposals
+    (4, 8, 12, 0.05, None, (1.0,), 2),        # noisy reads
+    (4, 8, 40, 0.0024, None, (1.0,), 3),      # headline shape
+    (4, 8, 400, 0.0024, None, (1.0,), 4),     # deep: large read counts, huge |llk|
+    (2, 12, 20, 0.01, 0.2, (1.0,), 5),
+    (6, 6, 30, 0.02, None, (0.3, 1.0), 6),    # heated chain accepts a lot
+    (4, 10, 25, 0.0024, 0.05, (0.1, 0.5, 1.0), 7),
+])
+def test_assemble_screening_stress_vs_oracle(dev, oracle, ploidy, n_pos, depth, error_rate, inbreeding, temps, seed):
+    """The float32 screening passes must never change a decision: long seeded runs over many
+    items (duplicated haplotypes, low / high depth, noisy reads) stay step-for-step identical."""
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.synth import _synth_from_haplotypes
+
+    rng = np.random.default_rng(seed)
+    n_items, steps = 40, 150
+    # true haplotypes drawn from a small pool so that duplicated haplotypes (dosage > 1) are common
+    pool = rng.integers(0, 2, size=(n_items, max(2, ploidy // 2 + 1), n_pos), dtype=np.int8)
+    pick = rng.integers(0, pool.shape[1], size=(n_items, ploidy))
+    haps = np.take_along_axis(pool, pick[:, :, None], axis=1)
+    batch = _synth_from_haplotypes(haps, depth, 2, error_rate, rng)
+    model = DenovoMCMC(ploidy=ploidy, n_alleles=[2] * n_pos, inbreeding=inbreeding, steps=steps, chains=2,
+                       temperatures=temps, random_seed=seed)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    out, results = model.fit_batch(reads, counts, return_results=True, raw=True)
+    for i in range(n_items):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], [2] * n_pos)
+        np.testing.assert_array_equal(out[i][0], ref["genotypes"], err_msg="item %d" % i)
+        close(out[i][1], ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+        assert results["llk_evals"][i] == ref["llk_evals"]
