@@ -58,7 +58,7 @@ struct AsmArgs {
     int32_t smem_per_warp;      // bytes
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
-        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs;
+        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache;
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
@@ -67,6 +67,17 @@ enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC
 // more needy sub-steps than this in one window: evaluate the window with the lane-parallel exact
 // loop instead of one exact evaluation per needy sub-step
 #define MCHB_EXACT_SERIAL_MAX 8
+
+// entries of the per-slot memo of screened structural steps (direct mapped)
+#define MCHB_SCACHE_N 128
+struct ScEntry {
+    uint32_t epoch;     // state epoch of the slot when the entry was filled
+    uint32_t key;       // (type, start, stop)
+    float smax;         // max over options of the screened mh (+inf: screening not conclusive)
+    float temp;         // inverse temperature the entry was computed for
+    int32_t n_options;
+    int32_t pad;
+};
 
 // nibble helpers for packed small-integer vectors (labels, SNP genotypes), P <= 16
 __device__ __forceinline__ int nib(uint64_t v, int i) { return (int)((v >> (4 * i)) & 15u); }
@@ -363,6 +374,23 @@ struct AsmCtx {
     __device__ __forceinline__ float *qrow32_lane(int s, int h) const { return q32() + (size_t)(s * P + h) * UPAD + lane; }
     __device__ __forceinline__ float *spare32_lane(int k) const { return q32() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
 
+    // ---- memo of screened quantities.  Chains sit in one state for long stretches; the screened
+    // (float32) acceptance bounds are functions of the state only, so they are kept per slot and
+    // dropped whenever the slot's state changes (epoch bump in commit / accept).
+    __device__ __forceinline__ uint32_t *epoch() const { return reinterpret_cast<uint32_t *>(sm + a.o_epoch); }  // [T] state, [T] mutation-memo
+    __device__ __forceinline__ double *mcache(int s) const {
+        return reinterpret_cast<double *>(sm + a.o_mcache) + (size_t)s * 2 * a.pmax * a.nmax;
+    }
+    __device__ __forceinline__ ScEntry *scache(int s) const {
+        return reinterpret_cast<ScEntry *>(sm + a.o_scache) + (size_t)s * MCHB_SCACHE_N;
+    }
+    __device__ __forceinline__ void bump_epoch(int s) {
+        uint32_t *e = epoch();
+        __syncwarp();
+        if (lane == 0) e[s] = e[s] + 1;
+        __syncwarp();
+    }
+
     // float32 per-read probability of the current state of slot s (sum of its shadow rows);
     // refreshed whenever a row of the slot changes for good
     __device__ __forceinline__ float *rpc_lane(int s) const { return reinterpret_cast<float *>(sm + a.o_rpc) + (size_t)s * UPAD + lane; }
@@ -411,6 +439,7 @@ struct AsmCtx {
         keys(s)[h] = k;
         compute_row<CH>(Rt() + lane, qrow_lane(s, h), qrow32_lane(s, h), k, geom());
         refresh_rpc(s);
+        bump_epoch(s);
     }
 
     // prior of the haplotype keys of a slot with up to two haplotypes replaced
@@ -560,8 +589,12 @@ struct AsmCtx {
         const double *q0 = q() + (size_t)(s * P) * UPAD;
         const double *cn = cnt();
         int done = 0;
+        const uint32_t epoch_at_start = epoch()[s];
 #pragma unroll 1
         while (done < n && !err) {
+            // screened quantities of this slot's sub-steps are still valid if the state is the
+            // one they were computed for
+            const bool memo_ok = epoch()[a.tmax + s] == epoch()[s];
             const int i = done + lane;
             const bool active = i < n;
             const int hj = pm[active ? i : done];
@@ -583,49 +616,65 @@ struct AsmCtx {
             }
             const bool mine = lane < limit;
             const uint64_t kn = (kh & ~((uint64_t)amask << shift)) | ((uint64_t)(cur ^ 1) << shift);
-            // ---- the parts of my Metropolis-Hastings ratio that do not need the likelihood
-            int copies_o = 0, copies_n = 1;
-#pragma unroll 1
-            for (int k = 0; k < P; k++) {
-                const uint64_t kk = ks[k];
-                copies_o += (kk == kh);
-                copies_n += (k != h && kk == kn);
-            }
-            double lprior_ratio = 0.0;
-            if (PRIOR) lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
-            const double lprop = LOG_INT[copies_n] - LOG_INT[copies_o];
             const double u = ws.double_at(2 * (mine ? lane : 0));
-            // ---- tier 1: float32 screening.  The proposal's row is the cached row of haplotype h
-            // times R[j][new] / R[j][old] (exact in real arithmetic); with float32 roundings and
-            // __logf the log-likelihood is off by < 5e-5 per read observation, far inside `margin`.
-            // The exact step accepts only if exp(min(0, mh)) reaches t = u (current allele 1) or
-            // t = 1 - u (current allele 0) — see the cumulative sums in base_step — so a sub-step
-            // whose screened mh is below log(t) - margin is certainly rejected and needs no exact
-            // evaluation; everything else ("needy") is decided exactly below.
-            double a32 = 0.0;
-            bool sane = true;
-            {
-                // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.  The
-                // subtraction hidden in it can lose relative accuracy when the proposal removes almost
-                // all of a read's probability, so reads with rp_new < 1e-4 rp_cur make the sub-step
-                // needy (exact path); above that the relative error stays below 1e-3 (in the margin).
-                const float *qh = q32() + (size_t)(s * P + h) * UPAD;
-                const float *rc = reinterpret_cast<const float *>(sm + a.o_rpc) + (size_t)s * UPAD;
-                const float *rt = rat() + (size_t)(j * 2 + (cur & 1)) * UPAD;
-                const float *cw = c32();
+            double lprior_ratio, lprop, d32;
+            double *mc = mcache(s) + 2 * (h * N + j);
+            if (memo_ok) {
+                // the state has not changed since these were computed
+                d32 = mc[0];
+                lprop = mc[1];
+                lprior_ratio = 0.0;  // folded into d32
+            } else {
+                // ---- the parts of my Metropolis-Hastings ratio that do not need the likelihood
+                int copies_o = 0, copies_n = 1;
+#pragma unroll 1
+                for (int k = 0; k < P; k++) {
+                    const uint64_t kk = ks[k];
+                    copies_o += (kk == kh);
+                    copies_n += (k != h && kk == kn);
+                }
+                lprior_ratio = 0.0;
+                if (PRIOR) lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
+                lprop = LOG_INT[copies_n] - LOG_INT[copies_o];
+                // ---- tier 1: float32 screening.  The proposal's row is the cached row of haplotype
+                // h times R[j][new] / R[j][old] (exact in real arithmetic); with float32 roundings and
+                // __logf the log-likelihood stays within `margin` of the exact one.  The exact step
+                // accepts only if exp(min(0, mh)) reaches t = u (current allele 1) or t = 1 - u
+                // (current allele 0) — see the cumulative sums in base_step — so a sub-step whose
+                // screened mh is below log(t) - margin is certainly rejected and needs no exact
+                // evaluation; everything else ("needy") is decided exactly below.
+                double a32 = 0.0;
+                bool sane = true;
+                {
+                    // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.
+                    // The subtraction hidden in it can lose relative accuracy when the proposal
+                    // removes almost all of a read's probability, so reads with rp_new < 1e-4 rp_cur
+                    // make the sub-step needy; above that the relative error stays below 1e-3.
+                    const float *qh = q32() + (size_t)(s * P + h) * UPAD;
+                    const float *rc = reinterpret_cast<const float *>(sm + a.o_rpc) + (size_t)s * UPAD;
+                    const float *rt = rat() + (size_t)(j * 2 + (cur & 1)) * UPAD;
+                    const float *cw = c32();
 #pragma unroll 4
-                for (int r = 0; r < U; r++) {
-                    const float rc_r = rc[r];
-                    const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
-                    sane = sane && (rp > 1e-4f * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
-                    a32 += (double)(__logf(rp) * cw[r]);
+                    for (int r = 0; r < U; r++) {
+                        const float rc_r = rc[r];
+                        const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
+                        sane = sane && (rp > 1e-4f * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
+                        a32 += (double)(__logf(rp) * cw[r]);
+                    }
+                }
+                d32 = sane ? (a32 - llk) + lprior_ratio : INFINITY;  // +inf: never screened out
+                if (mine) {
+                    mc[0] = d32;
+                    mc[1] = lprop;
                 }
             }
-            const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
+            const double mh32 = d32 * temp + lprop;
             const double t_acc = (cur == 1) ? u : 1.0 - u;
-            const bool hopeless = sane && (mh32 < (double)__logf((float)t_acc) - sc()[SC_MARGIN]) &&
+            const bool hopeless = (mh32 < (double)__logf((float)t_acc) - sc()[SC_MARGIN]) &&
                                   (u < 0.99999999999999911182);  // 1 - 2^-50: keep clear of the cs1 <= u corner
             const unsigned needy = __ballot_sync(MCHB_FULL, mine && !hopeless);
+            if (PRIOR && memo_ok && needy != 0)
+                lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
             if (__popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
                 // ---- tier 2a: exact decisions for the needy sub-steps, in order (uniform code)
                 int completed = limit;
@@ -667,6 +716,7 @@ struct AsmCtx {
                         ks[hl] = knl;  // the row is already installed
                         llk = llk_x;
                         refresh_rpc(s);
+                        bump_epoch(s);
                     }
                     break;
                 }
@@ -738,12 +788,33 @@ struct AsmCtx {
             commit(s, h1, kn1);
             __syncwarp();
         }
+        // every bi-allelic sub-step was screened from one and the same state: keep the memo
+        __syncwarp();
+        if (!err && epoch()[s] == epoch_at_start && lane == 0) epoch()[a.tmax + s] = epoch_at_start;
+        __syncwarp();
     }
 
     // ------------------------------------------------------------------ structural.py:434-587
     __device__ __forceinline__ void interval_step(int s, int start, int stop, int step_type, double temp,
                                                   double &llk) {
         uint64_t *ks = keys(s);
+        // ---- memo of this (type, interval) for the slot's current state
+        const uint32_t ep = epoch()[s];
+        const uint32_t skey = ((uint32_t)step_type << 16) | ((uint32_t)start << 8) | (uint32_t)stop;
+        ScEntry *ent = scache(s) + ((skey * 2654435761u) >> 25);
+        double u = 0.0;
+        bool have_u = false;
+        if (ent->epoch == ep && ent->key == skey && ent->temp == (float)temp) {
+            const int n_opt = ent->n_options;
+            if (n_opt == 0) return;  // no option, no draw
+            u = ws.next_double();
+            have_u = true;
+            if (u > 0.0 && u < 0.99999999999999911182 &&
+                (double)ent->smax < (double)__logf((float)u) - sc()[SC_MARGIN]) {
+                evals += n_opt;  // certainly "stay" (see the screening below)
+                return;
+            }
+        }
         const int width = B * (stop - start);
         uint64_t mask_in = 0;
         if (width >= 64) mask_in = ~0ull;
@@ -754,8 +825,18 @@ struct AsmCtx {
         __syncwarp();
         const int n_options = structural_options(lin, lout, P, step_type, o0, o1);
         __syncwarp();
-        if (n_options == 0) return;  // no draw (structural.py:504-506)
-        const double u = ws.next_double();  // the step's only draw (random_choice at the end)
+        if (n_options == 0) {  // no draw (structural.py:504-506)
+            if (lane == 0) {
+                ent->epoch = ep;
+                ent->key = skey;
+                ent->smax = INFINITY;
+                ent->temp = (float)temp;
+                ent->n_options = 0;
+            }
+            __syncwarp();
+            return;
+        }
+        if (!have_u) u = ws.next_double();  // the step's only draw (random_choice at the end)
         const double log_proposal = LOG_INV_INT[n_options];
         double lprior = 0.0;
         if (PRIOR) lprior = prior_of_keys(ks, -1, 0, -1, 0);
@@ -770,60 +851,73 @@ struct AsmCtx {
         // ---- float32 screening (all variable positions bi-allelic, <= 32 options): the step
         // stays put unless sum_i exp(min(0, mh_i)) / n exceeds u; with every screened mh_i below
         // log(u) - margin that sum is below u / e^2, so "stay" is certain and no exact
-        // log-likelihood is needed (same error budget as in mutation_compound_step).
-        if (B == 1 && n_options <= 32 && u > 0.0 && u < 0.99999999999999911182) {
-            const int n_ret = structural_options(my_lin, lout, P, step_type, nullptr, nullptr);
-            const double bound = (double)__logf((float)u) - sc()[SC_MARGIN];
-            const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
-            const float *rt = rat() + lane;
-            const float *cw = c32() + lane;
-            bool certain = true;
+        // log-likelihood is needed (same error budget as in mutation_compound_step).  The largest
+        // screened mh is a function of the state only and is kept in the memo.
+        {
+            double smax = INFINITY;
+            if (B == 1 && n_options <= 32) {
+                const int n_ret = structural_options(my_lin, lout, P, step_type, nullptr, nullptr);
+                const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
+                const float *rt = rat() + lane;
+                const float *cw = c32() + lane;
+                smax = -INFINITY;
 #pragma unroll 1
-            for (int k = 0; k < n_options && certain; k++) {
-                const int h0 = o0[k], h1 = o1[k];
-                const uint64_t k0 = ks[h0], k1 = ks[h1];
-                float ra[CH], rb[CH];
-#pragma unroll
-                for (int ch = 0; ch < CH; ch++) {
-                    ra[ch] = qs[h0 * UPAD + ch * 32];
-                    rb[ch] = qs[h1 * UPAD + ch * 32];
-                }
-                uint64_t d = (k0 ^ k1) & mask_in;  // positions where the swapped / copied segment differs
-#pragma unroll 1
-                while (d) {
-                    const int jp = __ffsll((long long)d) - 1;
-                    d &= d - 1;
-                    const int c0 = (int)((k0 >> jp) & 1ull);
+                for (int k = 0; k < n_options; k++) {
+                    const int h0 = o0[k], h1 = o1[k];
+                    const uint64_t k0 = ks[h0], k1 = ks[h1];
+                    float ra[CH], rb[CH];
 #pragma unroll
                     for (int ch = 0; ch < CH; ch++) {
-                        ra[ch] *= rt[(jp * 2 + c0) * UPAD + ch * 32];       // h0 takes h1's allele
-                        rb[ch] *= rt[(jp * 2 + (c0 ^ 1)) * UPAD + ch * 32]; // h1 takes h0's allele (recombination)
+                        ra[ch] = qs[h0 * UPAD + ch * 32];
+                        rb[ch] = qs[h1 * UPAD + ch * 32];
                     }
-                }
-                float acc = 0.f;
-                bool ok = true;
-#pragma unroll
-                for (int ch = 0; ch < CH; ch++) {
-                    float rp = 0.f;
+                    uint64_t d = (k0 ^ k1) & mask_in;  // positions where the swapped / copied segment differs
 #pragma unroll 1
-                    for (int hh = 0; hh < P; hh++) {
-                        float v = qs[hh * UPAD + ch * 32];
-                        v = (hh == h0) ? ra[ch] : v;
-                        v = (step_type == 0 && hh == h1) ? rb[ch] : v;
-                        rp += v;
+                    while (d) {
+                        const int jp = __ffsll((long long)d) - 1;
+                        d &= d - 1;
+                        const int c0 = (int)((k0 >> jp) & 1ull);
+#pragma unroll
+                        for (int ch = 0; ch < CH; ch++) {
+                            ra[ch] *= rt[(jp * 2 + c0) * UPAD + ch * 32];        // h0 takes h1's allele
+                            rb[ch] *= rt[(jp * 2 + (c0 ^ 1)) * UPAD + ch * 32];  // h1 takes h0's allele
+                        }
                     }
-                    ok = ok && (rp > 1e-30f) && (rp < 1e30f);
-                    acc += __logf(rp) * cw[ch * 32];
+                    float acc = 0.f;
+                    bool ok = true;
+#pragma unroll
+                    for (int ch = 0; ch < CH; ch++) {
+                        float rp = 0.f;
+#pragma unroll 1
+                        for (int hh = 0; hh < P; hh++) {
+                            float v = qs[hh * UPAD + ch * 32];
+                            v = (hh == h0) ? ra[ch] : v;
+                            v = (step_type == 0 && hh == h1) ? rb[ch] : v;
+                            rp += v;
+                        }
+                        ok = ok && (rp > 1e-30f) && (rp < 1e30f);
+                        acc += __logf(rp) * cw[ch * 32];
+                    }
+                    const double a32 = warp_sum((double)acc);
+                    const bool sane = __all_sync(MCHB_FULL, ok);
+                    double lprior_ratio = 0.0;
+                    if (PRIOR) lprior_ratio = prior_of_labels(__shfl_sync(MCHB_FULL, my_lin, k), lout) - lprior;
+                    const double lprop = LOG_INV_INT[__shfl_sync(MCHB_FULL, n_ret, k)] - log_proposal;
+                    const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
+                    smax = sane ? fmax(smax, mh32) : INFINITY;  // fmax ignores NaN: treat NaN as inconclusive
+                    if (isnan(mh32)) smax = INFINITY;
                 }
-                const double a32 = warp_sum((double)acc);
-                const bool sane = __all_sync(MCHB_FULL, ok);
-                double lprior_ratio = 0.0;
-                if (PRIOR) lprior_ratio = prior_of_labels(__shfl_sync(MCHB_FULL, my_lin, k), lout) - lprior;
-                const double lprop = LOG_INV_INT[__shfl_sync(MCHB_FULL, n_ret, k)] - log_proposal;
-                const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
-                certain = sane && (mh32 < bound);
             }
-            if (certain) {
+            __syncwarp();
+            if (lane == 0) {
+                ent->epoch = ep;
+                ent->key = skey;
+                ent->smax = __double2float_ru(smax);
+                ent->temp = (float)temp;
+                ent->n_options = n_options;
+            }
+            __syncwarp();
+            if (u > 0.0 && u < 0.99999999999999911182 && smax < (double)__logf((float)u) - sc()[SC_MARGIN]) {
                 evals += n_options;
                 return;
             }
@@ -1224,6 +1318,14 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     AsmCtx<CH, PRIOR> c(a, smem_raw + (size_t)warp * a.smem_per_warp, lane);
+    {
+        // state epochs start at 1 and only grow; memo entries start at epoch 0 (= never valid)
+        uint32_t *e = c.epoch();
+        for (int i = lane; i < 2 * a.tmax; i += 32) e[i] = i < a.tmax ? 1u : 0u;
+        ScEntry *sc0 = c.scache(0);
+        for (int i = lane; i < a.tmax * MCHB_SCACHE_N; i += 32) sc0[i].epoch = 0u;
+        __syncwarp();
+    }
 
     for (;;) {
         int w = 0;

@@ -381,6 +381,9 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_c32 = take(upad * 4, 4);
     args.o_rpc = take((size_t)g.tmax * upad * 4, 4);
     args.o_bcs = take((size_t)(g.maxopt + 1) * 8, 8);
+    args.o_epoch = take((size_t)g.tmax * 2 * 4, 4);
+    args.o_mcache = take((size_t)g.tmax * 2 * g.pmax * g.nmax * 8, 8);
+    args.o_scache = take((size_t)g.tmax * MCHB_SCACHE_N * sizeof(ScEntry), 8);
     return (off + 15) & ~(size_t)15;
 }
 
