@@ -569,18 +569,36 @@ struct AsmCtx {
         const int n = P * N;
         uint16_t *pm = perm();
         __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            int h = i / N, j = i - h * N;
-            pm[i] = (uint16_t)((h << 8) | j);
-        }
-        __syncwarp();
+        if (n <= 32) {
+            // np.random.shuffle of the rows with the permutation held one entry per lane
+            int pv = 0;
+            if (lane < n) {
+                const int h = lane / N;
+                pv = (h << 8) | (lane - h * N);
+            }
 #pragma unroll 1
-        for (int i = n - 1; i > 0; i--) {  // np.random.shuffle of the rows
-            int k = ws.randint(i + 1);
-            uint16_t x = pm[i], y = pm[k];
+            for (int i = n - 1; i > 0; i--) {
+                const int k = ws.randint(i + 1);
+                const int x = __shfl_sync(MCHB_FULL, pv, i);
+                const int y = __shfl_sync(MCHB_FULL, pv, k);
+                if (lane == i) pv = y;
+                if (lane == k) pv = x;
+            }
+            if (lane < n) pm[lane] = (uint16_t)pv;
+        } else {
+            for (int i = lane; i < n; i += 32) {
+                int h = i / N, j = i - h * N;
+                pm[i] = (uint16_t)((h << 8) | j);
+            }
             __syncwarp();
-            pm[i] = y;
-            pm[k] = x;
+#pragma unroll 1
+            for (int i = n - 1; i > 0; i--) {  // np.random.shuffle of the rows
+                int k = ws.randint(i + 1);
+                uint16_t x = pm[i], y = pm[k];
+                __syncwarp();
+                pm[i] = y;
+                pm[k] = x;
+            }
         }
         __syncwarp();
         const uint8_t *na = nall();
