@@ -27,7 +27,7 @@
 
 // resident CTAs per SM the register allocation is tuned for (4 warps per CTA)
 #ifndef MCHB_ASM_MINBLOCKS
-#define MCHB_ASM_MINBLOCKS 5
+#define MCHB_ASM_MINBLOCKS 4
 #endif
 
 namespace mchb {
