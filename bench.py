@@ -329,7 +329,7 @@ def run_b200(args, rank, world):
             "value": world * n_e2e * items_per_step * CHAINS * MCMC_STEPS / float(t[0]), "unit": UNIT,
             "h2d_bytes_per_step": int(h_reads.numel() * 8 + h_counts.numel() * 8 + h_nall.numel() + items.nbytes),
             "d2h_bytes_per_step": int(g_len + l_len * 8 + items_per_step * 24),
-            "steps": n_e2e, "note": "one handle, serial H2D -> kernels -> D2H of the full trace",
+            "steps": n_e2e, "note": "one handle, pinned host buffers: H2D, kernels in chunks of consecutive items, each chunk's trace D2H overlapping the next chunks' kernels",
         }
 
     # ---- roofline of the dominant kernel (assemble_kernel): FP64 SIMT pipe

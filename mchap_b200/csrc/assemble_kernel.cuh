@@ -570,21 +570,51 @@ struct AsmCtx {
         uint16_t *pm = perm();
         __syncwarp();
         if (n <= 32) {
-            // np.random.shuffle of the rows with the permutation held one entry per lane
-            int pv = 0;
-            if (lane < n) {
-                const int h = lane / N;
-                pv = (h << 8) | (lane - h * N);
-            }
+            // np.random.shuffle of the rows: for i = n-1 .. 1 swap rows i and randint(i + 1).
+            // (1) The draws.  Lane l looks at word cursor + l.  Which draw a word serves depends
+            // on how many words before it were rejected, so the rejection flags are iterated to
+            // their fixed point: a consistent assignment is unique (induction over the words), it
+            // is the serial rejection loop's, and word l is right after l + 1 rounds at the latest
+            // (in practice 2-4 rounds per 32 words).  Accepted draws are scattered to pm[i].
+            int i0 = n - 1;
+            const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
-            for (int i = n - 1; i > 0; i--) {
-                const int k = ws.randint(i + 1);
-                const int x = __shfl_sync(MCHB_FULL, pv, i);
-                const int y = __shfl_sync(MCHB_FULL, pv, k);
-                if (lane == i) pv = y;
-                if (lane == k) pv = x;
+            while (i0 > 0) {
+                const uint32_t w = ws.word_at(lane);
+                unsigned b = 0, bp;
+                int ik;
+                uint32_t v;
+                bool act;
+                do {
+                    bp = b;
+                    ik = i0 - lane + __popc(bp & lt);  // the draw this word would serve: randint(ik + 1)
+                    act = ik >= 1;
+                    v = w & (0xffffffffu >> __clz(act ? ik : 1));
+                    b = __ballot_sync(MCHB_FULL, act && (int)v > ik);
+                } while (b != bp);
+                const bool acc = act && !((b >> lane) & 1u);
+                if (acc) pm[ik] = (uint16_t)v;
+                const unsigned last = __ballot_sync(MCHB_FULL, acc && ik == 1);
+                const int used = last ? __ffs(last) : 32;
+                i0 = last ? 0 : i0 - (32 - __popc(b));
+                ws.advance(used);
             }
-            if (lane < n) pm[lane] = (uint16_t)pv;
+            __syncwarp();
+            // (2) The swaps.  Row i is final after swap i; what it receives is the content of row
+            // k_i at that time, traced back through the earlier swaps (i' > i) that moved something
+            // into that row.  Lane = final row.
+            const int kreg = (lane >= 1 && lane < n) ? (int)pm[lane] : 0;
+            int c = kreg;
+#pragma unroll 2
+            for (int ip = 1; ip < n; ip++) {
+                const int kk = __shfl_sync(MCHB_FULL, kreg, ip);
+                if (ip > lane && kk == c) c = ip;
+            }
+            __syncwarp();
+            if (lane < n) {
+                const int h = c / N;
+                pm[lane] = (uint16_t)((h << 8) | (c - h * N));
+            }
         } else {
             for (int i = lane; i < n; i += 32) {
                 int h = i / N, j = i - h * N;

@@ -19,6 +19,8 @@
 
 using namespace mchb;
 
+#define MCHB_MAX_CHUNKS 16
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -30,6 +32,9 @@ struct mchb_handle {
     int smem_optin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // rare shape classes run beside the main launch
+    cudaStream_t ks[4] = {nullptr, nullptr, nullptr, nullptr};  // chunked host path: two alternating stream pairs
+    cudaStream_t cs = nullptr;                                  // chunked host path: device-to-host copies
+    cudaEvent_t ev_chunk[2 * MCHB_MAX_CHUNKS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     float kernel_ms = 0.f;
@@ -174,6 +179,11 @@ void mchb_destroy(mchb_handle *h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (auto e : h->ev_chunk)
+        if (e) cudaEventDestroy(e);
+    for (auto st : h->ks)
+        if (st) cudaStreamDestroy(st);
+    if (h->cs) cudaStreamDestroy(h->cs);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -540,11 +550,33 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     }
     std::vector<int32_t> todo[NCLS];
     for (int c = 0; c < NCLS; c++) todo[c] = order[c];
+    // ---- host buffers: the batch is cut into chunks of consecutive items.  The chunks' launches
+    // alternate between two stream pairs, so the CTAs of chunk k + 1 take the SM slots that the tail
+    // of chunk k frees, while the copy stream moves the finished traces of chunk k to the host: the
+    // device-to-host transfer of the (large) trace hides behind the kernels of the next chunks.
+    int n_chunks = 1;
+    if (mem == MCHB_MEM_HOST && !pp.replay_words) {
+        const int64_t out_bytes = out_genotypes_len + 8 * out_llks_len;
+        n_chunks = (int)std::min<int64_t>({(int64_t)MCHB_MAX_CHUNKS, out_bytes >> 30, n_items / 4096});
+        if (const char *e = getenv("MCHB_HOST_CHUNKS"))  // test hook: force the chunk count
+            n_chunks = (int)std::min<int64_t>({(int64_t)MCHB_MAX_CHUNKS, (int64_t)atoi(e), n_items});
+        if (n_chunks < 1) n_chunks = 1;
+    }
+    if (n_chunks > 1 && !h->ks[0]) {
+        for (int k = 0; k < 4; k++) CK(cudaStreamCreateWithFlags(&h->ks[k], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+        for (int k = 0; k < 2 * MCHB_MAX_CHUNKS; k++) CK(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+    }
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8 * (size_t)n_chunks, &dcounter))) return rc;
+    int attempts_used = 0;
     for (int attempt = 0; attempt < 6; attempt++) {
         int64_t total = 0;
         for (int c = 0; c < NCLS; c++) total += (int64_t)todo[c].size();
         if (total == 0) break;
+        attempts_used++;
+        const int chunks = attempt == 0 ? n_chunks : 1;
         uint32_t *dwords = nullptr;
+        CK(cudaEventRecord(h->ev0, h->stream));  // the word-stream fill belongs to the timed device work
         if (pp.replay_words) {
             void *p;
             if ((rc = ensure(h, S_WORDS, sizeof(uint32_t) * (size_t)stream_len, &p))) return rc;
@@ -557,7 +589,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         }
         void *dorder;
         if ((rc = ensure(h, S_ORDER, sizeof(int32_t) * (size_t)total, &dorder))) return rc;
-        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8 * (size_t)chunks, h->stream));
         // the most populated class runs on the main stream; the rare classes are forked onto the
         // second stream first so that their few long-running warps overlap the main launch
         int main_cls = 0;
@@ -574,63 +606,109 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                 off += (int64_t)todo[c].size();
             }
         }
-        CK(cudaEventRecord(h->ev0, h->stream));
         CK(cudaEventRecord(h->ev_fork, h->stream));
-        CK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
         bool forked = false;
-        for (int pass = 0; pass < 2; pass++) {
-            for (int c = NCLS - 1; c >= 0; c--) {
-                if (todo[c].empty()) continue;
-                if ((pass == 0) == (c == main_cls)) continue;  // pass 0: rare classes, pass 1: main class
-                cudaStream_t st = (c == main_cls) ? h->stream : h->stream2;
-                if (c != main_cls) forked = true;
-                AsmArgs args;
-                memset(&args, 0, sizeof(args));
-                args.items = (const mchb_assemble_item *)ditems;
-                args.order = (int32_t *)dorder + offs[c];
-                args.n_order = (int32_t)todo[c].size();
-                args.reads = dreads;
-                args.counts = dcounts;
-                args.n_alleles = dnall;
-                args.initial = dinit;
-                args.out_genotypes = dog;
-                args.out_llks = dol;
-                args.results = (mchb_item_result *)dresults;
-                args.words = dwords;
-                args.item_stream = (const int32_t *)dstream;
-                args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
-                args.steps = pp.steps;
-                args.chains = pp.chains;
-                args.fix_homozygous = pp.fix_homozygous;
-                args.p_recomb = pp.p_recombination;
-                args.p_partial = pp.p_partial_dosage;
-                args.p_dosage = pp.p_dosage;
-                args.break_table = (const double *)dbreaks;
-                args.break_len = (const int32_t *)dbreaklen;
-                args.break_rows = pp.break_rows;
-                args.break_stride = pp.break_stride;
-                args.temperatures = (const double *)dtemps;
-                args.work_counter = (int32_t *)dcounter + c;
-                const int n_c = (int)todo[c].size();
-                switch (c) {
-                    case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c); break;
-                    case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c); break;
-                    case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c); break;
-                    case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c); break;
-                    case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c); break;
-                    case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c); break;
-                    case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c); break;
-                    default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c); break;
+        for (int k = 0; k < chunks; k++) {
+            const int64_t item_lo = n_items * k / chunks, item_hi = n_items * (k + 1) / chunks;
+            cudaStream_t st_main = chunks > 1 ? h->ks[2 * (k & 1)] : h->stream;
+            cudaStream_t st_rare = chunks > 1 ? h->ks[2 * (k & 1) + 1] : h->stream2;
+            if (chunks > 1 && k < 2) {
+                CK(cudaStreamWaitEvent(st_main, h->ev_fork, 0));
+                CK(cudaStreamWaitEvent(st_rare, h->ev_fork, 0));
+            } else if (chunks == 1) {
+                CK(cudaStreamWaitEvent(st_rare, h->ev_fork, 0));
+            }
+            for (int pass = 0; pass < 2; pass++) {
+                for (int c = NCLS - 1; c >= 0; c--) {
+                    if (todo[c].empty()) continue;
+                    if ((pass == 0) == (c == main_cls)) continue;  // pass 0: rare classes, pass 1: main class
+                    const int64_t lb = std::lower_bound(todo[c].begin(), todo[c].end(), (int32_t)item_lo) - todo[c].begin();
+                    const int64_t ub = std::lower_bound(todo[c].begin(), todo[c].end(), (int32_t)item_hi) - todo[c].begin();
+                    if (ub <= lb) continue;
+                    cudaStream_t st = (c == main_cls) ? st_main : st_rare;
+                    if (c != main_cls) forked = true;
+                    AsmArgs args;
+                    memset(&args, 0, sizeof(args));
+                    args.items = (const mchb_assemble_item *)ditems;
+                    args.order = (int32_t *)dorder + offs[c] + lb;
+                    args.n_order = (int32_t)(ub - lb);
+                    args.reads = dreads;
+                    args.counts = dcounts;
+                    args.n_alleles = dnall;
+                    args.initial = dinit;
+                    args.out_genotypes = dog;
+                    args.out_llks = dol;
+                    args.results = (mchb_item_result *)dresults;
+                    args.words = dwords;
+                    args.item_stream = (const int32_t *)dstream;
+                    args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
+                    args.steps = pp.steps;
+                    args.chains = pp.chains;
+                    args.fix_homozygous = pp.fix_homozygous;
+                    args.p_recomb = pp.p_recombination;
+                    args.p_partial = pp.p_partial_dosage;
+                    args.p_dosage = pp.p_dosage;
+                    args.break_table = (const double *)dbreaks;
+                    args.break_len = (const int32_t *)dbreaklen;
+                    args.break_rows = pp.break_rows;
+                    args.break_stride = pp.break_stride;
+                    args.temperatures = (const double *)dtemps;
+                    args.work_counter = (int32_t *)dcounter + 8 * k + c;
+                    const int n_c = (int)(ub - lb);
+                    switch (c) {
+                        case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c); break;
+                        case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c); break;
+                        case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c); break;
+                        case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c); break;
+                        case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c); break;
+                        case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c); break;
+                        case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c); break;
+                        default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c); break;
+                    }
+                    if (rc) return rc;
                 }
-                if (rc) return rc;
+            }
+            if (chunks > 1) {
+                CK(cudaEventRecord(h->ev_chunk[2 * k], st_main));
+                CK(cudaEventRecord(h->ev_chunk[2 * k + 1], st_rare));
             }
         }
-        if (forked) {
+        // join the kernel streams into the main stream (ev1 = all kernels done)
+        if (chunks > 1) {
+            for (int k = std::max(0, chunks - 2); k < chunks; k++) {
+                CK(cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * k], 0));
+                CK(cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * k + 1], 0));
+            }
+        } else if (forked) {
             CK(cudaEventRecord(h->ev_join, h->stream2));
             CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         }
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+        // the chunk copies are queued after every launch, so that a pageable destination (whose
+        // copies block the host) still overlaps with the kernels already in the streams
+        if (chunks > 1) {
+            for (int k = 0; k < chunks; k++) {
+                const int64_t item_lo = n_items * k / chunks, item_hi = n_items * (k + 1) / chunks;
+                int64_t g_lo = INT64_MAX, g_hi = 0, l_lo = INT64_MAX, l_hi = 0;
+                for (int64_t i = item_lo; i < item_hi; i++) {
+                    const mchb_assemble_item &it = items[i];
+                    const int64_t gsz = (int64_t)pp.chains * pp.steps * it.ploidy * it.n_pos;
+                    g_lo = std::min(g_lo, it.genotypes_off);
+                    g_hi = std::max(g_hi, it.genotypes_off + gsz);
+                    l_lo = std::min(l_lo, it.llks_off);
+                    l_hi = std::max(l_hi, it.llks_off + (int64_t)pp.chains * pp.steps);
+                }
+                CK(cudaStreamWaitEvent(h->cs, h->ev_chunk[2 * k], 0));
+                CK(cudaStreamWaitEvent(h->cs, h->ev_chunk[2 * k + 1], 0));
+                if (g_hi > g_lo)
+                    CK(cudaMemcpyAsync(out_genotypes + g_lo, dog + g_lo, (size_t)(g_hi - g_lo), cudaMemcpyDeviceToHost, h->cs));
+                if (l_hi > l_lo)
+                    CK(cudaMemcpyAsync(out_llks + l_lo, dol + l_lo, sizeof(double) * (size_t)(l_hi - l_lo),
+                                       cudaMemcpyDeviceToHost, h->cs));
+            }
+            CK(cudaStreamSynchronize(h->cs));
+        }
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -648,7 +726,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         if (!again) break;
         stream_len *= 2;
     }
-    if (mem == MCHB_MEM_HOST) {
+    if (mem == MCHB_MEM_HOST && (n_chunks == 1 || attempts_used > 1)) {
         CK(cudaMemcpyAsync(out_genotypes, dog, (size_t)out_genotypes_len, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(out_llks, dol, sizeof(double) * (size_t)out_llks_len, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -995,6 +1073,7 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
     std::vector<int32_t> todo = order;
     for (int attempt = 0; attempt < 6 && !todo.empty(); attempt++) {
         uint32_t *dwords = nullptr;
+        CK(cudaEventRecord(h->ev0, h->stream));  // the word-stream fill belongs to the timed device work
         if (pp.replay_words) {
             void *p;
             if ((rc = ensure(h, S_WORDS, sizeof(uint32_t) * (size_t)stream_len, &p))) return rc;
@@ -1033,7 +1112,6 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
         a.smem_per_warp = (int32_t)per_warp;
         long long want = ((long long)todo.size() + warps_per_cta - 1) / warps_per_cta;
         long long grid = std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
-        CK(cudaEventRecord(h->ev0, h->stream));
         call_mcmc_kernel<<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev1, h->stream));

@@ -200,6 +200,38 @@ def test_assemble_per_item_seeds_and_ragged_alleles(dev, oracle):
         assert results["rng_words"][i] == ref["words"]
 
 
+def test_assemble_chunked_host_pipeline(dev, oracle, monkeypatch):
+    """Host buffers, batch cut into chunks whose trace copies overlap the next chunks' kernels:
+    same bytes as the single-launch path and as the oracle (classes CH=1 and CH=2 mixed)."""
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.synth import synth_items
+
+    shallow = synth_items(40, ploidy=4, n_pos=8, depth=30, seed=3)
+    deep = synth_items(13, ploidy=4, n_pos=8, depth=90, seed=4)
+    reads = [shallow.item(i)[0] for i in range(40)] + [deep.item(i)[0] for i in range(13)]
+    counts = [shallow.item(i)[1] for i in range(40)] + [deep.item(i)[1] for i in range(13)]
+    order = np.random.default_rng(0).permutation(len(reads))
+    reads = [reads[i] for i in order]
+    counts = [counts[i] for i in order]
+    model = DenovoMCMC(ploidy=4, n_alleles=[2] * 8, steps=80, chains=2, random_seed=5)
+    monkeypatch.delenv("MCHB_HOST_CHUNKS", raising=False)
+    whole, res_w = model.fit_batch(reads, counts, return_results=True, raw=True)
+    assert dev.last_kernel_launches <= 3
+    for n_chunks in (2, 5, 16):
+        monkeypatch.setenv("MCHB_HOST_CHUNKS", str(n_chunks))
+        piped, res_p = model.fit_batch(reads, counts, return_results=True, raw=True)
+        assert dev.last_kernel_launches > 3
+        for i in range(len(reads)):
+            np.testing.assert_array_equal(piped[i][0], whole[i][0], err_msg="item %d" % i)
+            np.testing.assert_array_equal(piped[i][1], whole[i][1])
+        np.testing.assert_array_equal(res_p["rng_words"], res_w["rng_words"])
+    monkeypatch.delenv("MCHB_HOST_CHUNKS")
+    for i in (0, 17, 52):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], [2] * 8)
+        np.testing.assert_array_equal(whole[i][0], ref["genotypes"])
+        close(whole[i][1], ref["llks"])
+
+
 def test_replay_harness(dev, oracle):
     """Both implementations driven by the same pre-drawn word stream (not an MT19937 stream)."""
     from mchap_b200 import DenovoMCMC
