@@ -317,9 +317,11 @@ def run_b200(args, rank, world):
         n_e2e = min(K, 3)
         barrier()
         t0 = time.perf_counter()
+        e2e_kernel_ms = 0.0
         for _ in range(n_e2e):
             host_step()
             launches_e2e = dev.last_kernel_launches
+            e2e_kernel_ms += dev.last_kernel_ms
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=gpu)
@@ -329,7 +331,8 @@ def run_b200(args, rank, world):
             "value": world * n_e2e * items_per_step * CHAINS * MCMC_STEPS / float(t[0]), "unit": UNIT,
             "h2d_bytes_per_step": int(h_reads.numel() * 8 + h_counts.numel() * 8 + h_nall.numel() + items.nbytes),
             "d2h_bytes_per_step": int(g_len + l_len * 8 + items_per_step * 24),
-            "steps": n_e2e, "note": "one handle, pinned host buffers: H2D, kernels in chunks of consecutive items, each chunk's trace D2H overlapping the next chunks' kernels",
+            "steps": n_e2e, "ms_per_step": 1e3 * float(t[0]) / n_e2e, "kernel_ms_per_step": e2e_kernel_ms / n_e2e,
+            "host_chunks": dev.last_host_chunks, "note": "one handle, pinned host buffers: H2D, kernels in chunks of consecutive items, each chunk's trace D2H overlapping the next chunks' kernels",
         }
 
     # ---- roofline of the dominant kernel (assemble_kernel): FP64 SIMT pipe

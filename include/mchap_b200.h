@@ -72,6 +72,9 @@ void mchb_get_limits(mchb_limits *out);
  * how many kernels this library launched in it */
 float mchb_last_kernel_ms(const mchb_handle *h);
 int32_t mchb_last_kernel_launches(const mchb_handle *h);
+/* host-buffer assemble calls: into how many chunks the last call cut the trace copy (1 = one
+ * copy after the kernels; > 1 = chunk copies overlapped with the kernels) */
+int32_t mchb_last_host_chunks(const mchb_handle *h);
 /* the cudaStream_t the handle launches on (for external event timing) */
 void *mchb_stream(const mchb_handle *h);
 int mchb_sm_count(const mchb_handle *h);

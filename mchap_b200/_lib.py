@@ -147,7 +147,7 @@ _lock = threading.Lock()
 # exported symbols declared in include/mchap_b200.h
 SYMBOLS = [
     "mchb_create", "mchb_destroy", "mchb_last_error", "mchb_get_limits", "mchb_last_kernel_ms",
-    "mchb_last_kernel_launches", "mchb_stream", "mchb_sm_count", "mchb_mt19937_words",
+    "mchb_last_kernel_launches", "mchb_last_host_chunks", "mchb_stream", "mchb_sm_count", "mchb_mt19937_words",
     "mchb_genotype_rank", "mchb_genotype_unrank", "mchb_log_likelihood_batch",
     "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
@@ -181,6 +181,8 @@ def load():
         L.mchb_last_kernel_ms.argtypes = [vp]
         L.mchb_last_kernel_launches.restype = C.c_int32
         L.mchb_last_kernel_launches.argtypes = [vp]
+        L.mchb_last_host_chunks.restype = C.c_int32
+        L.mchb_last_host_chunks.argtypes = [vp]
         L.mchb_stream.restype = vp
         L.mchb_stream.argtypes = [vp]
         L.mchb_sm_count.restype = C.c_int

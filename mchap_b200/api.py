@@ -87,6 +87,10 @@ class Device:
         return int(self._lib.mchb_last_kernel_launches(self._h))
 
     @property
+    def last_host_chunks(self):
+        return int(self._lib.mchb_last_host_chunks(self._h))
+
+    @property
     def sm_count(self):
         return int(self._lib.mchb_sm_count(self._h))
 

@@ -53,6 +53,11 @@ struct AsmArgs {
     int32_t break_rows, break_stride;
     const double *temperatures;
     int32_t *work_counter;
+    // host-buffer path: items finished per chunk of chunk_items consecutive item ids; the copy
+    // stream waits on these counters (stream memory operation) before moving a chunk's traces
+    uint32_t *chunk_done;       // may be null
+    uint32_t *chunk_flags;      // host-mapped: set to 1 by the warp that finishes a chunk's last item
+    int32_t chunk_items, n_items;
     // shared memory geometry (per warp)
     int32_t nmax, amax, pmax, tmax, maxopt;
     int32_t smem_per_warp;      // bytes
@@ -1363,6 +1368,11 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
 template <int CH, bool PRIOR>
 __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const __grid_constant__ AsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // The launches of one call (rare shape classes first, the most populated class last) are
+    // chained with programmatic dependent launch: the next kernel may start as soon as every CTA
+    // of this one is resident, so the few long-running rare items start first and the big class
+    // fills the rest of the machine, all in one stream.  (There is no data dependency.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     AsmCtx<CH, PRIOR> c(a, smem_raw + (size_t)warp * a.smem_per_warp, lane);
@@ -1537,6 +1547,19 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
             r.rng_words = c.ws.cur;
             r.llk_evals = c.evals;
             a.results[item_id] = r;
+        }
+        if (a.chunk_done) {
+            __threadfence_system();  // every lane: its trace stores are visible before the count moves
+            __syncwarp();
+            if (lane == 0) {
+                const int k = item_id / a.chunk_items;
+                const uint32_t target = (uint32_t)min(a.chunk_items, a.n_items - k * a.chunk_items);
+                if (atomicAdd(a.chunk_done + k, 1u) + 1u == target) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile uint32_t *>(a.chunk_flags + k) = 1u;
+                    __threadfence_system();
+                }
+            }
         }
         __syncwarp();
     }

@@ -19,7 +19,9 @@
 
 using namespace mchb;
 
-#define MCHB_MAX_CHUNKS 16
+#define MCHB_MAX_CHUNKS 64
+// cuStreamWaitValue32(stream, device address, value, flags): flags 0 = wait until *addr >= value
+typedef int (*wait_value32_fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
 
 struct DevBuf {
     void *p = nullptr;
@@ -31,14 +33,14 @@ struct mchb_handle {
     int sm_count = 0;
     int smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;  // rare shape classes run beside the main launch
-    cudaStream_t ks[4] = {nullptr, nullptr, nullptr, nullptr};  // chunked host path: two alternating stream pairs
-    cudaStream_t cs = nullptr;                                  // chunked host path: device-to-host copies
-    cudaEvent_t ev_chunk[2 * MCHB_MAX_CHUNKS] = {};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t cs = nullptr;       // chunked host path: device-to-host copies behind wait-value operations
+    wait_value32_fn wait_value32 = nullptr;
+    uint32_t *chunk_flags = nullptr;  // pinned, device-mapped host memory: one "chunk finished" flag per chunk
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;
     std::string err;
     float kernel_ms = 0.f;
     int32_t launches = 0;
+    int32_t host_chunks = 1;
     std::vector<DevBuf> bufs;  // scratch slots, grown on demand
 };
 
@@ -47,7 +49,7 @@ namespace {
 enum Slot {
     S_ITEMS = 0, S_ORDER, S_READS, S_COUNTS, S_NALLELES, S_INITIAL, S_OUT_G, S_OUT_L, S_RESULTS,
     S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
-    S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS,
+    S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS, S_CHUNKS,
     S_NSLOTS
 };
 
@@ -134,6 +136,7 @@ void begin_call(mchb_handle *h) {
     h->err.clear();
     h->kernel_ms = 0.f;
     h->launches = 0;
+    h->host_chunks = 1;
 }
 
 }  // namespace
@@ -154,10 +157,8 @@ int mchb_create(int device, mchb_handle **out) {
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
     h->bufs.resize(S_NSLOTS);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
         delete h;
         return MCHB_ERR_CUDA;
     }
@@ -178,13 +179,8 @@ void mchb_destroy(mchb_handle *h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    for (auto e : h->ev_chunk)
-        if (e) cudaEventDestroy(e);
-    for (auto st : h->ks)
-        if (st) cudaStreamDestroy(st);
     if (h->cs) cudaStreamDestroy(h->cs);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->chunk_flags) cudaFreeHost(h->chunk_flags);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -202,6 +198,7 @@ void mchb_get_limits(mchb_limits *out) {
 
 float mchb_last_kernel_ms(const mchb_handle *h) { return h ? h->kernel_ms : 0.f; }
 int32_t mchb_last_kernel_launches(const mchb_handle *h) { return h ? h->launches : 0; }
+int32_t mchb_last_host_chunks(const mchb_handle *h) { return h ? h->host_chunks : 0; }
 void *mchb_stream(const mchb_handle *h) { return h ? (void *)h->stream : nullptr; }
 int mchb_sm_count(const mchb_handle *h) { return h ? h->sm_count : 0; }
 
@@ -398,7 +395,8 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
 }
 
 template <int CH, bool PRIOR>
-int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const AsmGeom &g, int n_items_class) {
+int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const AsmGeom &g, int n_items_class,
+                    bool overlap_previous) {
     const size_t per_warp = asm_layout(g, CH, args);
     int warps_per_cta = 4;
     while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
@@ -420,7 +418,18 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
     args.tmax = g.tmax;
     args.maxopt = g.maxopt;
     args.smem_per_warp = (int)per_warp;
-    assemble_kernel<CH, PRIOR><<<(unsigned)grid, warps_per_cta * 32, smem, stream>>>(args);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(warps_per_cta * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap_previous ? 1 : 0;  // start once the previous kernel's CTAs are all resident
+    CK(cudaLaunchKernelEx(&cfg, assemble_kernel<CH, PRIOR>, args));
     CK(cudaGetLastError());
     h->launches++;
     return MCHB_OK;
@@ -550,31 +559,63 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     }
     std::vector<int32_t> todo[NCLS];
     for (int c = 0; c < NCLS; c++) todo[c] = order[c];
-    // ---- host buffers: the batch is cut into chunks of consecutive items.  The chunks' launches
-    // alternate between two stream pairs, so the CTAs of chunk k + 1 take the SM slots that the tail
-    // of chunk k frees, while the copy stream moves the finished traces of chunk k to the host: the
-    // device-to-host transfer of the (large) trace hides behind the kernels of the next chunks.
+    // ---- host buffers: the batch is cut into chunks of consecutive item ids.  Every launch counts
+    // the items it finishes per chunk (device counters); the warp that finishes the last item of a
+    // chunk raises the chunk's flag in device-mapped host memory, and the copy stream waits on that
+    // flag with a stream memory operation (cuStreamWaitValue32) before it moves the chunk's traces
+    // to the host.  The device-to-host transfer of the (large) trace so hides behind the sampling
+    // of the later chunks, with one launch per class and no tail between chunks.  (Waiting on the
+    // device counters themselves was measured not to release before the kernels end.)
     int n_chunks = 1;
+    int64_t chunk_items = n_items;
     if (mem == MCHB_MEM_HOST && !pp.replay_words) {
         const int64_t out_bytes = out_genotypes_len + 8 * out_llks_len;
-        n_chunks = (int)std::min<int64_t>({(int64_t)MCHB_MAX_CHUNKS, out_bytes >> 30, n_items / 4096});
+        n_chunks = (int)std::min<int64_t>({(int64_t)MCHB_MAX_CHUNKS, out_bytes >> 28, n_items / 1024});
         if (const char *e = getenv("MCHB_HOST_CHUNKS"))  // test hook: force the chunk count
             n_chunks = (int)std::min<int64_t>({(int64_t)MCHB_MAX_CHUNKS, (int64_t)atoi(e), n_items});
         if (n_chunks < 1) n_chunks = 1;
+        if (n_chunks > 1 && !h->wait_value32) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+                q != cudaDriverEntryPointSuccess || !fn) {
+                (void)cudaGetLastError();
+                n_chunks = 1;  // no stream memory operations: one copy after the kernels
+            } else {
+                h->wait_value32 = (wait_value32_fn)fn;
+            }
+        }
+        if (n_chunks > 1 && !h->cs) {
+            CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+            CK(cudaHostAlloc((void **)&h->chunk_flags, sizeof(uint32_t) * MCHB_MAX_CHUNKS, cudaHostAllocMapped));
+        }
+        chunk_items = (n_items + n_chunks - 1) / n_chunks;
+        n_chunks = (int)((n_items + chunk_items - 1) / chunk_items);
     }
-    if (n_chunks > 1 && !h->ks[0]) {
-        for (int k = 0; k < 4; k++) CK(cudaStreamCreateWithFlags(&h->ks[k], cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
-        for (int k = 0; k < 2 * MCHB_MAX_CHUNKS; k++) CK(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+    h->host_chunks = n_chunks;
+    void *dchunk = nullptr;
+    std::vector<uint32_t> chunk_skip((size_t)n_chunks, 0u);
+    if (n_chunks > 1) {
+        if ((rc = ensure(h, S_CHUNKS, sizeof(uint32_t) * (size_t)n_chunks, &dchunk))) return rc;
+        // items that no launch handles count as finished from the start
+        std::vector<uint8_t> launched((size_t)n_items, 0);
+        for (int c = 0; c < NCLS; c++)
+            for (int32_t id : order[c]) launched[(size_t)id] = 1;
+        for (int64_t i = 0; i < n_items; i++)
+            if (!launched[(size_t)i]) chunk_skip[(size_t)(i / chunk_items)]++;
+        // no kernel of an earlier call is running any more: the flags can be written directly
+        for (int k = 0; k < n_chunks; k++) {
+            const int64_t size_k = std::min<int64_t>(n_items, chunk_items * (k + 1)) - chunk_items * k;
+            h->chunk_flags[k] = chunk_skip[(size_t)k] >= (uint64_t)size_k ? 1u : 0u;
+        }
     }
-    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8 * (size_t)n_chunks, &dcounter))) return rc;
     int attempts_used = 0;
     for (int attempt = 0; attempt < 6; attempt++) {
         int64_t total = 0;
         for (int c = 0; c < NCLS; c++) total += (int64_t)todo[c].size();
         if (total == 0) break;
         attempts_used++;
-        const int chunks = attempt == 0 ? n_chunks : 1;
+        const bool piped = attempt == 0 && n_chunks > 1;
         uint32_t *dwords = nullptr;
         CK(cudaEventRecord(h->ev0, h->stream));  // the word-stream fill belongs to the timed device work
         if (pp.replay_words) {
@@ -589,9 +630,12 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         }
         void *dorder;
         if ((rc = ensure(h, S_ORDER, sizeof(int32_t) * (size_t)total, &dorder))) return rc;
-        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8 * (size_t)chunks, h->stream));
-        // the most populated class runs on the main stream; the rare classes are forked onto the
-        // second stream first so that their few long-running warps overlap the main launch
+        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+        if (piped)
+            CK(cudaMemcpyAsync(dchunk, chunk_skip.data(), sizeof(uint32_t) * (size_t)n_chunks, cudaMemcpyHostToDevice,
+                               h->stream));
+        // rare classes first, the most populated class last, chained by programmatic dependent
+        // launch (see assemble_kernel): the few long-running rare items overlap the main launch
         int main_cls = 0;
         for (int c = 1; c < NCLS; c++)
             if (todo[c].size() > todo[main_cls].size()) main_cls = c;
@@ -606,90 +650,74 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                 off += (int64_t)todo[c].size();
             }
         }
-        CK(cudaEventRecord(h->ev_fork, h->stream));
-        bool forked = false;
-        for (int k = 0; k < chunks; k++) {
-            const int64_t item_lo = n_items * k / chunks, item_hi = n_items * (k + 1) / chunks;
-            cudaStream_t st_main = chunks > 1 ? h->ks[2 * (k & 1)] : h->stream;
-            cudaStream_t st_rare = chunks > 1 ? h->ks[2 * (k & 1) + 1] : h->stream2;
-            if (chunks > 1 && k < 2) {
-                CK(cudaStreamWaitEvent(st_main, h->ev_fork, 0));
-                CK(cudaStreamWaitEvent(st_rare, h->ev_fork, 0));
-            } else if (chunks == 1) {
-                CK(cudaStreamWaitEvent(st_rare, h->ev_fork, 0));
-            }
-            for (int pass = 0; pass < 2; pass++) {
-                for (int c = NCLS - 1; c >= 0; c--) {
-                    if (todo[c].empty()) continue;
-                    if ((pass == 0) == (c == main_cls)) continue;  // pass 0: rare classes, pass 1: main class
-                    const int64_t lb = std::lower_bound(todo[c].begin(), todo[c].end(), (int32_t)item_lo) - todo[c].begin();
-                    const int64_t ub = std::lower_bound(todo[c].begin(), todo[c].end(), (int32_t)item_hi) - todo[c].begin();
-                    if (ub <= lb) continue;
-                    cudaStream_t st = (c == main_cls) ? st_main : st_rare;
-                    if (c != main_cls) forked = true;
-                    AsmArgs args;
-                    memset(&args, 0, sizeof(args));
-                    args.items = (const mchb_assemble_item *)ditems;
-                    args.order = (int32_t *)dorder + offs[c] + lb;
-                    args.n_order = (int32_t)(ub - lb);
-                    args.reads = dreads;
-                    args.counts = dcounts;
-                    args.n_alleles = dnall;
-                    args.initial = dinit;
-                    args.out_genotypes = dog;
-                    args.out_llks = dol;
-                    args.results = (mchb_item_result *)dresults;
-                    args.words = dwords;
-                    args.item_stream = (const int32_t *)dstream;
-                    args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
-                    args.steps = pp.steps;
-                    args.chains = pp.chains;
-                    args.fix_homozygous = pp.fix_homozygous;
-                    args.p_recomb = pp.p_recombination;
-                    args.p_partial = pp.p_partial_dosage;
-                    args.p_dosage = pp.p_dosage;
-                    args.break_table = (const double *)dbreaks;
-                    args.break_len = (const int32_t *)dbreaklen;
-                    args.break_rows = pp.break_rows;
-                    args.break_stride = pp.break_stride;
-                    args.temperatures = (const double *)dtemps;
-                    args.work_counter = (int32_t *)dcounter + 8 * k + c;
-                    const int n_c = (int)(ub - lb);
-                    switch (c) {
-                        case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c); break;
-                        case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c); break;
-                        case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c); break;
-                        case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c); break;
-                        case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c); break;
-                        case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c); break;
-                        case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c); break;
-                        default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c); break;
-                    }
-                    if (rc) return rc;
-                }
-            }
-            if (chunks > 1) {
-                CK(cudaEventRecord(h->ev_chunk[2 * k], st_main));
-                CK(cudaEventRecord(h->ev_chunk[2 * k + 1], st_rare));
-            }
+        if (piped) {
+            CK(cudaEventRecord(h->ev_fork, h->stream));
+            CK(cudaStreamWaitEvent(h->cs, h->ev_fork, 0));
         }
-        // join the kernel streams into the main stream (ev1 = all kernels done)
-        if (chunks > 1) {
-            for (int k = std::max(0, chunks - 2); k < chunks; k++) {
-                CK(cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * k], 0));
-                CK(cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * k + 1], 0));
+        bool chained = false;
+        for (int pass = 0; pass < 2; pass++) {
+            for (int c = NCLS - 1; c >= 0; c--) {
+                if (todo[c].empty()) continue;
+                if ((pass == 0) == (c == main_cls)) continue;  // pass 0: rare classes, pass 1: main class
+                cudaStream_t st = h->stream;
+                AsmArgs args;
+                memset(&args, 0, sizeof(args));
+                args.items = (const mchb_assemble_item *)ditems;
+                args.order = (int32_t *)dorder + offs[c];
+                args.n_order = (int32_t)todo[c].size();
+                args.reads = dreads;
+                args.counts = dcounts;
+                args.n_alleles = dnall;
+                args.initial = dinit;
+                args.out_genotypes = dog;
+                args.out_llks = dol;
+                args.results = (mchb_item_result *)dresults;
+                args.words = dwords;
+                args.item_stream = (const int32_t *)dstream;
+                args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
+                args.steps = pp.steps;
+                args.chains = pp.chains;
+                args.fix_homozygous = pp.fix_homozygous;
+                args.p_recomb = pp.p_recombination;
+                args.p_partial = pp.p_partial_dosage;
+                args.p_dosage = pp.p_dosage;
+                args.break_table = (const double *)dbreaks;
+                args.break_len = (const int32_t *)dbreaklen;
+                args.break_rows = pp.break_rows;
+                args.break_stride = pp.break_stride;
+                args.temperatures = (const double *)dtemps;
+                args.work_counter = (int32_t *)dcounter + c;
+                args.chunk_done = piped ? (uint32_t *)dchunk : nullptr;
+                args.chunk_items = (int32_t)chunk_items;
+                args.n_items = (int32_t)n_items;
+                if (piped) {
+                    void *dflags = nullptr;
+                    CK(cudaHostGetDevicePointer(&dflags, h->chunk_flags, 0));
+                    args.chunk_flags = (uint32_t *)dflags;
+                }
+                const int n_c = (int)todo[c].size();
+                switch (c) {
+                    case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c, chained); break;
+                    case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c, chained); break;
+                    case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c, chained); break;
+                    case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c, chained); break;
+                    case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c, chained); break;
+                    case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c, chained); break;
+                    case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c, chained); break;
+                    default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c, chained); break;
+                }
+                if (rc) return rc;
+                chained = true;
             }
-        } else if (forked) {
-            CK(cudaEventRecord(h->ev_join, h->stream2));
-            CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         }
         CK(cudaEventRecord(h->ev1, h->stream));
-        CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
-        // the chunk copies are queued after every launch, so that a pageable destination (whose
+        // the chunk copies are queued after the launches, so that a pageable destination (whose
         // copies block the host) still overlaps with the kernels already in the streams
-        if (chunks > 1) {
-            for (int k = 0; k < chunks; k++) {
-                const int64_t item_lo = n_items * k / chunks, item_hi = n_items * (k + 1) / chunks;
+        if (piped) {
+            const bool trace_chunks = getenv("MCHB_TRACE_CHUNKS") != nullptr;  // debugging aid: when did each copy end
+            std::vector<cudaEvent_t> tev;
+            for (int k = 0; k < n_chunks; k++) {
+                const int64_t item_lo = chunk_items * k, item_hi = std::min<int64_t>(n_items, chunk_items * (k + 1));
                 int64_t g_lo = INT64_MAX, g_hi = 0, l_lo = INT64_MAX, l_hi = 0;
                 for (int64_t i = item_lo; i < item_hi; i++) {
                     const mchb_assemble_item &it = items[i];
@@ -699,16 +727,54 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                     l_lo = std::min(l_lo, it.llks_off);
                     l_hi = std::max(l_hi, it.llks_off + (int64_t)pp.chains * pp.steps);
                 }
-                CK(cudaStreamWaitEvent(h->cs, h->ev_chunk[2 * k], 0));
-                CK(cudaStreamWaitEvent(h->cs, h->ev_chunk[2 * k + 1], 0));
+                void *dflags = nullptr;
+                CK(cudaHostGetDevicePointer(&dflags, h->chunk_flags, 0));
+                if (trace_chunks && k == 0) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    CK(cudaEventRecord(e, h->cs));
+                    tev.push_back(e);
+                }
+                if (h->wait_value32(h->cs, (unsigned long long)((uint32_t *)dflags + k), 1u, 0u)) {
+                    h->err = "cuStreamWaitValue32 failed";
+                    return MCHB_ERR_CUDA;
+                }
+                if (trace_chunks) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    CK(cudaEventRecord(e, h->cs));
+                    tev.push_back(e);
+                }
                 if (g_hi > g_lo)
                     CK(cudaMemcpyAsync(out_genotypes + g_lo, dog + g_lo, (size_t)(g_hi - g_lo), cudaMemcpyDeviceToHost, h->cs));
                 if (l_hi > l_lo)
                     CK(cudaMemcpyAsync(out_llks + l_lo, dol + l_lo, sizeof(double) * (size_t)(l_hi - l_lo),
                                        cudaMemcpyDeviceToHost, h->cs));
+                if (trace_chunks) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreate(&e));
+                    CK(cudaEventRecord(e, h->cs));
+                    tev.push_back(e);
+                }
             }
             CK(cudaStreamSynchronize(h->cs));
+            if (trace_chunks) {
+                CK(cudaStreamSynchronize(h->stream));
+                float t1 = 0.f;
+                CK(cudaEventElapsedTime(&t1, h->ev0, h->ev1));
+                fprintf(stderr, "[mchb] kernels done at %.1f ms; chunk copies done at:", t1);
+                for (cudaEvent_t e : tev) {
+                    float t = 0.f;
+                    CK(cudaEventElapsedTime(&t, h->ev0, e));
+                    fprintf(stderr, " %.1f", t);
+                    cudaEventDestroy(e);
+                }
+                fprintf(stderr, "\n");
+            }
         }
+        // (queued behind the chunk copies: a copy that waits for the kernels at the head of the
+        // device-to-host queue would hold the chunk copies back)
+        CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
