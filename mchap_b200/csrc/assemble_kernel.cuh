@@ -63,7 +63,8 @@ struct AsmArgs {
     int32_t smem_per_warp;      // bytes
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
-        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache;
+        o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache,
+        o_wmap;
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
@@ -617,7 +618,8 @@ struct AsmCtx {
             }
             __syncwarp();
             if (lane < n) {
-                const int h = c / N;
+                // c / N for c < 32: (c + 0.5) / N is at least 1 / (2 N) away from an integer
+                const int h = __float2int_rz(((float)c + 0.5f) * __frcp_rn((float)N));
                 pm[lane] = (uint16_t)((h << 8) | (c - h * N));
             }
         } else {
@@ -707,7 +709,7 @@ struct AsmCtx {
                     const float *rc = reinterpret_cast<const float *>(sm + a.o_rpc) + (size_t)s * UPAD;
                     const float *rt = rat() + (size_t)(j * 2 + (cur & 1)) * UPAD;
                     const float *cw = c32();
-#pragma unroll 4
+#pragma unroll 2
                     for (int r = 0; r < U; r++) {
                         const float rc_r = rc[r];
                         const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
@@ -1428,6 +1430,20 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
         }
         if (N > 0 && !status) {
             const uint8_t *het = c.het();
+            // how each byte of a recorded genotype is produced: 0x8000 | haplotype << 8 | key shift
+            // for a variable position, the fixed allele otherwise
+            uint16_t *wmap = reinterpret_cast<uint16_t *>(c.sm + a.o_wmap);
+            {
+                const uint8_t *fixa = c.fixa();
+                __syncwarp();
+                for (int i = lane; i < step_sz; i += 32) wmap[i] = (uint16_t)fixa[i % Nf];
+                __syncwarp();
+                for (int i = lane; i < P * N; i += 32) {
+                    const int h = i / N, k = i - h * N;
+                    wmap[h * Nf + het[k]] = (uint16_t)(0x8000 | (h << 8) | (c.B * k));
+                }
+                __syncwarp();
+            }
             double *dist = c.dist(), *opr = c.opr();
             const int brow_i = min(N, a.break_rows - 1);
             const double *brow = a.break_table + (size_t)brow_i * a.break_stride;
@@ -1520,17 +1536,13 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
                     // ---- record the cold chain (state of the last temperature, mcmc.py:418-425)
                     {
                         const uint64_t *ks = c.keys(c.slot(T - 1));
-                        const uint8_t *fixa = c.fixa();
                         int8_t *dst = ogc + (size_t)step * step_sz;
                         __syncwarp();
+#pragma unroll 1
                         for (int i = lane; i < step_sz; i += 32) {
-                            int h = i / Nf, j = i - h * Nf;
-                            dst[i] = (int8_t)fixa[j];
-                        }
-                        __syncwarp();
-                        for (int i = lane; i < P * N; i += 32) {
-                            int h = i / N, k = i - h * N;
-                            dst[h * Nf + het[k]] = (int8_t)((uint32_t)(ks[h] >> (c.B * k)) & c.amask);
+                            const uint32_t m = wmap[i];
+                            const uint32_t v = (uint32_t)(ks[(m >> 8) & 0x7f] >> (m & 63)) & c.amask;
+                            dst[i] = (int8_t)((m & 0x8000u) ? v : m);
                         }
                         if (lane == 0) olc[step] = llk;
                         __syncwarp();

@@ -36,6 +36,15 @@ __constant__ float LOGF_INT[MCHB_TABLE_N];
 // without touching global memory.  The cursor is warp-uniform.
 // Reference semantics: numba/cpython/randomimpl.py get_next_int32 109-132.
 // ---------------------------------------------------------------------------------------
+// One copy of the ring refill for all its call sites (instruction-cache footprint): lane l loads
+// word blk * 32 + l of the stream (0 past its end) into the slot of block blk.
+__device__ __noinline__ void word_ring_refill(const uint32_t *base, uint32_t *ring, int len, int blk, int lane) {
+    const int i = blk * 32 + lane;
+    __syncwarp();
+    ring[(blk & 3) * 32 + lane] = (i < len) ? __ldg(base + i) : 0u;
+    __syncwarp();
+}
+
 struct WordStream {
     const uint32_t *base;
     uint32_t *ring;   // shared memory, 128 words
@@ -60,12 +69,7 @@ struct WordStream {
     }
     __device__ __forceinline__ bool exhausted() const { return cur > len; }
     // the cursor just entered block cur/32: fetch block cur/32 + 2 into the slot of block cur/32 - 2
-    __device__ __forceinline__ void refill() {
-        const int blk = (cur >> 5) + 2;
-        __syncwarp();
-        ring[(blk & 3) * 32 + lane] = load_block(blk);
-        __syncwarp();
-    }
+    __device__ __forceinline__ void refill() { word_ring_refill(base, ring, len, (cur >> 5) + 2, lane); }
     __device__ __forceinline__ uint32_t next_u32() {
         const uint32_t w = ring[cur & 127];
         cur++;
