@@ -64,7 +64,7 @@ struct AsmArgs {
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
         o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache,
-        o_wmap;
+        o_wmap, o_inv;
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
@@ -608,13 +608,28 @@ struct AsmCtx {
             __syncwarp();
             // (2) The swaps.  Row i is final after swap i; what it receives is the content of row
             // k_i at that time, traced back through the earlier swaps (i' > i) that moved something
-            // into that row.  Lane = final row.
+            // into that row: c = k_i; for i' = i + 1 .. n - 1: if (k_i' == c) c = i'.  With
+            // inv[x] = {i' : k_i' == x} the first hop is the lowest member of inv[k_i] above i and
+            // every later hop is succ(c) = the lowest member of inv[c] above c.  Lane = final row.
             const int kreg = (lane >= 1 && lane < n) ? (int)pm[lane] : 0;
+            uint32_t *inv = reinterpret_cast<uint32_t *>(sm + a.o_inv);  // 32 words
+            inv[lane] = 0u;
+            __syncwarp();
+            if (lane >= 1 && lane < n) atomicOr(inv + kreg, 1u << lane);
+            __syncwarp();
+            const uint32_t above = 0xfffffffeu << lane;  // lanes above mine
+            const uint32_t mine_in = inv[lane] & above;
+            const int succ = mine_in ? __ffs(mine_in) - 1 : -1;
             int c = kreg;
-#pragma unroll 2
-            for (int ip = 1; ip < n; ip++) {
-                const int kk = __shfl_sync(MCHB_FULL, kreg, ip);
-                if (ip > lane && kk == c) c = ip;
+            {
+                const uint32_t first = __shfl_sync(MCHB_FULL, inv[lane], kreg) & above;
+                int nxt = first ? __ffs(first) - 1 : -1;
+#pragma unroll 1
+                while (__any_sync(MCHB_FULL, nxt >= 0)) {
+                    if (nxt >= 0) c = nxt;
+                    const int s2 = __shfl_sync(MCHB_FULL, succ, c);
+                    nxt = nxt >= 0 ? s2 : -1;
+                }
             }
             __syncwarp();
             if (lane < n) {

@@ -392,6 +392,7 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_mcache = take((size_t)g.tmax * 2 * g.pmax * g.nmax * 8, 8);
     args.o_scache = take((size_t)g.tmax * MCHB_SCACHE_N * sizeof(ScEntry), 8);
     args.o_wmap = take((size_t)g.pmax * g.nmax * 2, 2);
+    args.o_inv = take(32 * 4, 4);
     return (off + 15) & ~(size_t)15;
 }
 
