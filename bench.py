@@ -38,6 +38,10 @@ WORKLOAD = ("synthetic tetraploid assemble: 10k loci x 8 SNVs x 100 samples, dep
             "2 chains x 1500 steps")
 
 
+# DRAM bytes per (locus, sample) item of assemble_kernel<1,false>, from the committed ncu capture
+# (profiles/README.md): 253.8 MB read + written by a launch of 1964 items (traces dominate)
+NCU_DRAM_BYTES_PER_ITEM = 129226.0
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -336,6 +340,7 @@ def run_b200(args, rank, world):
         }
 
     # ---- roofline of the dominant kernel (assemble_kernel): FP64 SIMT pipe
+    main_items_per_launch = int(np.mean([(b.n_reads() <= 32).sum() for b, _ in batches]))
     peak_tf = dev.measure_fp64_peak()
     achieved_tf = flops / dev_time / 1e12
     in_bytes = sum(x[0].numel() * 8 + x[1].numel() * 8 for x in dev_in) / K
@@ -347,7 +352,12 @@ def run_b200(args, rank, world):
         pass
     roofline = {
         "bound": "fp64_simt", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+        "frac": achieved_tf / peak_tf if peak_tf else None,
+        "traffic": NCU_DRAM_BYTES_PER_ITEM * main_items_per_launch, "traffic_per_item": NCU_DRAM_BYTES_PER_ITEM,
+        "traffic_source": "profiles/r01_final_ncu_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) of one "
+                          "`ncu --set full` launch of assemble_kernel<1,false> / its 1964 items, scaled to the "
+                          "%d items of this bench's main-class launch; algorithmic bytes per item = %.0f" % (
+                              main_items_per_launch, (in_bytes + out_bytes) / items_per_step),
         "peak_source": "DFMA probe kernel measured live in this run (MEASURED_PEAKS.json holds no FP64 figure)",
         "kernel": "assemble_kernel<1>", "llk_evals_per_mcmc_step": evals / (K * items_per_step * CHAINS * MCMC_STEPS),
         "hbm_achieved_gbs": (in_bytes + out_bytes) / (dev_time / K) / 1e9,
