@@ -42,6 +42,7 @@ extern "C" {
 #define MCHB_ITEM_INITIAL_SHAPE 5  /* reference: AssertionError, assemble/mcmc.py:207 */
 #define MCHB_ITEM_RNG_EXHAUSTED 6  /* pre-drawn word stream too short (the host shim retries with a longer one) */
 #define MCHB_ITEM_UNSUPPORTED 8    /* shape outside the compiled limits (see mchb_limits); never silently approximated */
+#define MCHB_ITEM_TALLY_OVERFLOW 9 /* trace tally: more distinct genotypes than max_unique (call again with a larger table) */
 
 #define MCHB_MEM_HOST 0
 #define MCHB_MEM_DEVICE 1
@@ -239,6 +240,54 @@ int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcmc_params *p
                          int64_t freqs_len, const int32_t *initial, int32_t pstride,
                          int32_t *out_alleles, int64_t out_alleles_len, double *out_llks,
                          int64_t out_llks_len, mchb_item_result *results);
+
+/* ---- trace post-processing (tallies of a de novo assembly trace) ---------------------------
+ * Replaces, for a batch of traces: assemble/classes.py:265-278 GenotypeMultiTrace.__post_init__
+ * (per-step lexicographic haplotype sort, encoding/integer/sequence.py:78-110), 280-305 burn,
+ * 307-325 posterior and 327-339 split (unique genotypes in first-occurrence order and their
+ * counts, mset.py:242-284, 361-392) — the inputs of mode_genotype_support (classes.py:87-128)
+ * and replicate_incongruence (341-376).
+ *
+ * Item i: trace int8[chains, steps, ploidy, n_pos] at genotypes + genotypes_off (haplotypes in
+ * any order).  Steps burn..steps-1 of every chain are tallied.  Outputs, per item:
+ *   out_states int8[max_unique, ploidy, n_pos] at states_off: the distinct genotypes, haplotypes
+ *     sorted, in order of first occurrence in the chain-major flattened trace;
+ *   out_counts int32[max_unique, chains] at tallies_off: occurrences of state u in chain c;
+ *   out_first  int32[max_unique, chains] at tallies_off: step (after burn) of the first
+ *     occurrence of state u in chain c, -1 if it never occurs there (the per-chain
+ *     first-occurrence order);
+ *   results[i].n_het = number of distinct genotypes; status MCHB_ITEM_TALLY_OVERFLOW if there
+ *     are more than max_unique (the arrays then hold the first max_unique states, counts are
+ *     incomplete). */
+typedef struct {
+    int64_t genotypes_off;   /* int8 elements into genotypes */
+    int64_t states_off;      /* int8 elements into out_states */
+    int64_t tallies_off;     /* int32 elements into out_counts and out_first */
+    int32_t n_pos, ploidy, chains, steps;
+    int32_t burn, max_unique;
+} mchb_tally_item;
+
+/* mem_in: where `genotypes` lives; mem_out: where the three output arrays live. */
+int mchb_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items,
+                           int64_t n_items, const int8_t *genotypes, int64_t genotypes_len,
+                           int8_t *out_states, int64_t out_states_len, int32_t *out_counts,
+                           int32_t *out_first, int64_t tallies_len, mchb_item_result *results);
+
+/* mchb_assemble_batch followed by mchb_trace_tally_batch with the trace kept on the device: the
+ * inputs and the tallies are HOST memory, the traces never leave HBM (they live in the handle's
+ * scratch; items[i].genotypes_off / llks_off index that scratch like in mchb_assemble_batch and
+ * tally_items[i].genotypes_off must repeat items[i].genotypes_off).  This is the call behind
+ * `DenovoMCMC(...).fit(...).burn(n).posterior()` of mchap/application/assemble.py:123-170 for
+ * a batch.  results: the assemble results; tally_results: the tally results. */
+int mchb_assemble_tally_batch(mchb_handle *h, const mchb_assemble_params *params,
+                              const mchb_assemble_item *items, const mchb_tally_item *tally_items,
+                              int64_t n_items, const double *reads, int64_t reads_len,
+                              const int64_t *counts, int64_t counts_len, const int8_t *n_alleles,
+                              int64_t n_alleles_len, const int8_t *initial, int64_t initial_len,
+                              int64_t genotypes_len, int64_t llks_len, int8_t *out_states,
+                              int64_t out_states_len, int32_t *out_counts, int32_t *out_first,
+                              int64_t tallies_len, mchb_item_result *results,
+                              mchb_item_result *tally_results);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ ITEM_CHOICE_RANGE = 4
 ITEM_INITIAL_SHAPE = 5
 ITEM_RNG_EXHAUSTED = 6
 ITEM_UNSUPPORTED = 8
+ITEM_TALLY_OVERFLOW = 9
 
 MEM_HOST = 0
 MEM_DEVICE = 1
@@ -95,6 +96,20 @@ class CallItem(C.Structure):
     ]
 
 
+class TallyItem(C.Structure):
+    _fields_ = [
+        ("genotypes_off", C.c_int64),
+        ("states_off", C.c_int64),
+        ("tallies_off", C.c_int64),
+        ("n_pos", C.c_int32),
+        ("ploidy", C.c_int32),
+        ("chains", C.c_int32),
+        ("steps", C.c_int32),
+        ("burn", C.c_int32),
+        ("max_unique", C.c_int32),
+    ]
+
+
 class CallMcmcParams(C.Structure):
     _fields_ = [
         ("steps", C.c_int32),
@@ -151,6 +166,7 @@ SYMBOLS = [
     "mchb_genotype_rank", "mchb_genotype_unrank", "mchb_log_likelihood_batch",
     "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
+    "mchb_trace_tally_batch", "mchb_assemble_tally_batch",
 ]
 
 
@@ -221,6 +237,15 @@ def load():
         L.mchb_call_mcmc_batch.argtypes = [
             vp, C.c_int, C.POINTER(CallMcmcParams), vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
             vp, C.c_int64, vp, C.c_int32, vp, C.c_int64, vp, C.c_int64, vp,
+        ]
+        L.mchb_trace_tally_batch.restype = C.c_int
+        L.mchb_trace_tally_batch.argtypes = [
+            vp, C.c_int, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp,
+        ]
+        L.mchb_assemble_tally_batch.restype = C.c_int
+        L.mchb_assemble_tally_batch.argtypes = [
+            vp, C.POINTER(AssembleParams), vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
+            vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp,
         ]
         _lib = L
         return _lib

@@ -12,6 +12,7 @@ from . import _lib as L
 ASSEMBLE_ITEM_DTYPE = L._np_dtype(L.AssembleItem)
 LLK_ITEM_DTYPE = L._np_dtype(L.LlkItem)
 ITEM_RESULT_DTYPE = L._np_dtype(L.ItemResult)
+TALLY_ITEM_DTYPE = L._np_dtype(L.TallyItem)
 CALL_ITEM_DTYPE = L._np_dtype(L.CallItem)
 
 _ITEM_ERRORS = {
@@ -245,6 +246,34 @@ class Device:
             _ptr(out_llks), int(lens[5]), _ptr(results))
         self._check(rc)
         return results
+
+
+    # ------------------------------------------------------------------ N1 trace tallies
+    def trace_tally_call(self, items, genotypes, genotypes_len, out_states, out_counts, out_first,
+                         mem_in=L.MEM_HOST, mem_out=L.MEM_HOST):
+        """Thin wrapper of mchb_trace_tally_batch (items: structured array of TALLY_ITEM_DTYPE)."""
+        n = len(items)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        rc = self._lib.mchb_trace_tally_batch(
+            self._h, mem_in, mem_out, _ptr(items), n, _ptr(genotypes), int(genotypes_len), _ptr(out_states),
+            int(out_states.size), _ptr(out_counts), _ptr(out_first), int(out_counts.size), _ptr(results))
+        self._check(rc)
+        return results
+
+    def assemble_tally_call(self, items, tally_items, params, reads, counts, n_alleles, initial, lens,
+                            out_states, out_counts, out_first):
+        """Thin wrapper of mchb_assemble_tally_batch: host inputs, traces stay on the device, host
+        tallies.  ``lens`` = (reads_len, counts_len, n_alleles_len, initial_len, genotypes_len, llks_len)."""
+        n = len(items)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        tally_results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        rc = self._lib.mchb_assemble_tally_batch(
+            self._h, C.byref(params), _ptr(items), _ptr(tally_items), n, _ptr(reads), int(lens[0]), _ptr(counts),
+            int(lens[1]), _ptr(n_alleles), int(lens[2]), _ptr(initial), int(lens[3]), int(lens[4]), int(lens[5]),
+            _ptr(out_states), int(out_states.size), _ptr(out_counts), _ptr(out_first), int(out_counts.size),
+            _ptr(results), _ptr(tally_results))
+        self._check(rc)
+        return results, tally_results
 
 
 def count_genotypes(n_haplotypes, ploidy):

@@ -172,15 +172,65 @@ class GenotypeMultiTrace(object):
 
     def replicate_incongruence(self, threshold=0.6):
         """0: chains agree; 1: different modes; 2: more than ploidy haplotypes among the modes."""
-        modes = [t.posterior().mode_genotype_support() for t in self.split()]
-        alleles = [m.alleles() for m in modes if m.probabilities.sum() >= threshold]
-        if len({a.tobytes() for a in alleles}) <= 1:
-            return 0
-        ploidy = len(alleles[0])
-        union = {}
-        for a in alleles:  # multiset union: max multiplicity per haplotype
-            haps, counts, _, _ = unique_first_occurrence(a)
-            for h, c in zip(haps, counts):
-                k = h.tobytes()
-                union[k] = max(union.get(k, 0), int(c))
-        return 2 if sum(union.values()) > ploidy else 1
+        return _replicate_incongruence([t.posterior() for t in self.split()], threshold)
+
+
+def _replicate_incongruence(chain_posteriors, threshold):
+    """classes.py:341-376 of the reference on the per-chain posteriors."""
+    modes = [p.mode_genotype_support() for p in chain_posteriors]
+    alleles = [m.alleles() for m in modes if m.probabilities.sum() >= threshold]
+    if len({a.tobytes() for a in alleles}) <= 1:
+        return 0
+    ploidy = len(alleles[0])
+    union = {}
+    for a in alleles:  # multiset union: max multiplicity per haplotype
+        haps, counts, _, _ = unique_first_occurrence(a)
+        for h, c in zip(haps, counts):
+            k = h.tobytes()
+            union[k] = max(union.get(k, 0), int(c))
+    return 2 if sum(union.values()) > ploidy else 1
+
+
+@dataclass
+class TraceTally(object):
+    """What a burnt GenotypeMultiTrace is reduced to before any of its summaries is taken, computed
+    on the device by mchb_trace_tally_batch: the distinct genotypes (haplotypes sorted) in order of
+    first occurrence in the chain-major flattened trace, how often each occurs in every chain, and
+    the step of its first occurrence in every chain (-1: never).
+
+    ``posterior()``, ``split()`` and ``replicate_incongruence()`` return what the same methods of the
+    burnt trace return (reference: mchap/assemble/classes.py:307-376)."""
+
+    states: np.ndarray   # int8[n_unique, ploidy, n_positions]
+    counts: np.ndarray   # int64[n_unique, n_chains]
+    first: np.ndarray    # int64[n_unique, n_chains]
+
+    @classmethod
+    def from_trace(cls, trace):
+        """Host-side tally of a (sorted, burnt) GenotypeMultiTrace: same content as the device's."""
+        n_chain, n_step, ploidy, n_base = trace.genotypes.shape
+        flat = trace.genotypes.reshape(n_chain * n_step, ploidy, n_base)
+        states, _, _, labels = unique_first_occurrence(flat)
+        labels = labels.reshape(n_chain, n_step)
+        counts = np.zeros((len(states), n_chain), dtype=np.int64)
+        first = np.full((len(states), n_chain), -1, dtype=np.int64)
+        for c in range(n_chain):
+            u, idx, cnt = np.unique(labels[c], return_index=True, return_counts=True)
+            counts[u, c] = cnt
+            first[u, c] = idx
+        return cls(np.array(states, dtype=np.int8), counts, first)
+
+    def posterior(self):
+        totals = self.counts.sum(axis=1)
+        probs = totals / np.sum(totals)
+        idx = np.flip(np.argsort(probs))
+        return PosteriorGenotypeDistribution(self.states[idx], probs[idx])
+
+    def split(self):
+        for c in range(self.counts.shape[1]):
+            seen = np.flatnonzero(self.counts[:, c] > 0)
+            seen = seen[np.argsort(self.first[seen, c], kind="stable")]  # the chain's own first-occurrence order
+            yield TraceTally(self.states[seen], self.counts[seen, c:c + 1], self.first[seen, c:c + 1])
+
+    def replicate_incongruence(self, threshold=0.6):
+        return _replicate_incongruence([t.posterior() for t in self.split()], threshold)

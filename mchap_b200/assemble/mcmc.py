@@ -9,8 +9,10 @@ from dataclasses import dataclass
 import numpy as np
 
 from .. import _lib as L
-from ..api import ASSEMBLE_ITEM_DTYPE, default_device, make_assemble_params, raise_item_status
-from .classes import GenotypeMultiTrace
+from ..api import (ASSEMBLE_ITEM_DTYPE, TALLY_ITEM_DTYPE, default_device, make_assemble_params,
+                   raise_item_status)
+from .._lib import ITEM_TALLY_OVERFLOW as TALLY_OVERFLOW
+from .classes import GenotypeMultiTrace, TraceTally
 
 __all__ = ["DenovoMCMC", "point_beta_probabilities", "break_table"]
 
@@ -40,6 +42,10 @@ def break_table(n_pos, alpha=1.0, beta=3.0, n_intervals=None):
         table[n, : len(row)] = row
         lens[n] = len(row)
     return table, lens
+
+
+def sub2(lst, idx):
+    return None if lst is None else [lst[i] for i in idx]
 
 
 @dataclass
@@ -82,14 +88,8 @@ class DenovoMCMC(object):
         res = self.fit_batch([reads], [read_counts], None if initial is None else [initial])
         return res[0]
 
-    def fit_batch(self, reads_list, counts_list=None, initial_list=None, n_alleles_list=None,
-                  seeds=None, return_results=False, raw=False, replay_words=None):
-        """Run ``fit`` for many items in one device call.
-
-        n_alleles_list: per item allele counts (default: self.n_alleles for every item);
-        seeds: per item seeds (default: self.random_seed for every item, like the CLIs);
-        raw=True returns unsorted (genotypes, llks) arrays instead of GenotypeMultiTrace."""
-        dev = self.device or default_device()
+    def _pack(self, reads_list, counts_list, initial_list, n_alleles_list, seeds):
+        """Flat input arrays + item descriptors of a batch (outputs laid out item after item)."""
         n = len(reads_list)
         temps = self._temperatures()
         items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
@@ -139,17 +139,35 @@ class DenovoMCMC(object):
         nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
         counts = np.concatenate(cs) if use_counts and cs else None
         initial = np.concatenate(ins) if ins else None
+        return dict(items=items, shapes=shapes, reads=reads, counts=counts, n_alleles=nall, initial=initial,
+                    nmax=nmax, genotypes_len=go, llks_len=lo,
+                    lens=(reads.size, 0 if counts is None else counts.size, nall.size,
+                          0 if initial is None else initial.size))
+
+    def _params(self, nmax, replay_words=None):
+        table, lens = break_table(nmax, self.alpha, self.beta, self.n_intervals)
+        return make_assemble_params(
+            self.steps, self.chains, self.fix_homozygous, self.recombination_step_probability,
+            self.partial_dosage_step_probability, self.dosage_step_probability, table, lens, self._temperatures(),
+            replay_words=replay_words)
+
+    def fit_batch(self, reads_list, counts_list=None, initial_list=None, n_alleles_list=None,
+                  seeds=None, return_results=False, raw=False, replay_words=None):
+        """Run ``fit`` for many items in one device call.
+
+        n_alleles_list: per item allele counts (default: self.n_alleles for every item);
+        seeds: per item seeds (default: self.random_seed for every item, like the CLIs);
+        raw=True returns unsorted (genotypes, llks) arrays instead of GenotypeMultiTrace."""
+        dev = self.device or default_device()
+        n = len(reads_list)
+        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds)
+        items, shapes, go, lo = pk["items"], pk["shapes"], pk["genotypes_len"], pk["llks_len"]
         out_g = np.zeros(max(go, 1), dtype=np.int8)
         out_l = np.full(max(lo, 1), np.nan, dtype=np.float64)
-        table, lens = break_table(nmax, self.alpha, self.beta, self.n_intervals)
-        params, keep = make_assemble_params(
-            self.steps, self.chains, self.fix_homozygous, self.recombination_step_probability,
-            self.partial_dosage_step_probability, self.dosage_step_probability, table, lens, temps,
-            replay_words=replay_words)
+        params, keep = self._params(pk["nmax"], replay_words)
         results = dev.assemble_call(
-            items, params, reads, counts, nall, initial, out_g, out_l,
-            (reads.size, 0 if counts is None else counts.size, nall.size, 0 if initial is None else initial.size,
-             go, lo))
+            items, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"], out_g, out_l,
+            pk["lens"] + (go, lo))
         out = []
         for i, (N, g0, l0) in enumerate(shapes):
             raise_item_status(int(results["status"][i]), i if n > 1 else None)
@@ -161,4 +179,64 @@ class DenovoMCMC(object):
             out.append((g, l) if raw else GenotypeMultiTrace(g, l))
         if return_results:
             return out, results
+        return out
+
+    def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None,
+                            n_alleles_list=None, seeds=None, max_unique=64):
+        """``fit(...).burn(burn)`` for many items with the traces kept on the device: returns one
+        TraceTally per item (``.posterior()``, ``.split()``, ``.replicate_incongruence()`` behave
+        like the burnt GenotypeMultiTrace of the reference, mchap/application/assemble.py:123-170).
+
+        Only the tallies (distinct genotypes, counts and first occurrences per chain) cross the
+        bus; an item with more than ``max_unique`` distinct genotypes is redone with a table as
+        large as its trace."""
+        dev = self.device or default_device()
+        n = len(reads_list)
+        out = [None] * n
+        todo = list(range(n))
+        table = int(max_unique)
+        kept = max(self.steps - max(int(burn), 0), 0) * self.chains
+        while todo:
+            sub = lambda lst: None if lst is None else [lst[i] for i in todo]
+            pk = self._pack(sub(reads_list), sub(counts_list), sub(initial_list), sub(n_alleles_list), sub(seeds))
+            items = pk["items"]
+            m = len(items)
+            titems = np.zeros(m, dtype=TALLY_ITEM_DTYPE)
+            pn = items["ploidy"].astype(np.int64) * items["n_pos"].astype(np.int64)
+            titems["genotypes_off"] = items["genotypes_off"]
+            titems["n_pos"], titems["ploidy"] = items["n_pos"], items["ploidy"]
+            titems["chains"], titems["steps"], titems["burn"] = self.chains, self.steps, int(burn)
+            titems["max_unique"] = table
+            titems["states_off"] = np.concatenate([[0], np.cumsum(pn * table)[:-1]])
+            titems["tallies_off"] = np.arange(m, dtype=np.int64) * table * self.chains
+            out_states = np.zeros(max(int((pn * table).sum()), 1), dtype=np.int8)
+            out_counts = np.zeros(max(m * table * self.chains, 1), dtype=np.int32)
+            out_first = np.zeros_like(out_counts)
+            params, keep = self._params(pk["nmax"])
+            results, tres = dev.assemble_tally_call(
+                items, titems, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"],
+                pk["lens"] + (pk["genotypes_len"], pk["llks_len"]), out_states, out_counts, out_first)
+            again = []
+            for k, i in enumerate(todo):
+                raise_item_status(int(results["status"][k]), i if n > 1 else None)
+                if int(tres["status"][k]) == TALLY_OVERFLOW:
+                    again.append(i)
+                    continue
+                raise_item_status(int(tres["status"][k]), i if n > 1 else None)
+                u = int(tres["n_het"][k])
+                P, N = int(items["ploidy"][k]), int(items["n_pos"][k])
+                so, to = int(titems["states_off"][k]), int(titems["tallies_off"][k])
+                out[i] = TraceTally(
+                    out_states[so: so + u * P * N].reshape(u, P, N).copy(),
+                    out_counts[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64),
+                    out_first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64))
+            if again and table >= min(kept, 8192):
+                # more distinct genotypes than the device table can hold: tally those on the host
+                traces = self.fit_batch(sub2(reads_list, again), sub2(counts_list, again), sub2(initial_list, again),
+                                        sub2(n_alleles_list, again), sub2(seeds, again))
+                for i, t in zip(again, traces):
+                    out[i] = TraceTally.from_trace(t.burn(int(burn)))
+                again = []
+            todo = again
+            table = max(1, min(kept, 8192))
         return out

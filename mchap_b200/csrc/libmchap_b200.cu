@@ -16,6 +16,7 @@
 #include "assemble_kernel.cuh"
 #include "exact_kernel.cuh"
 #include "call_mcmc_kernel.cuh"
+#include "tally_kernel.cuh"
 
 using namespace mchb;
 
@@ -50,6 +51,7 @@ enum Slot {
     S_ITEMS = 0, S_ORDER, S_READS, S_COUNTS, S_NALLELES, S_INITIAL, S_OUT_G, S_OUT_L, S_RESULTS,
     S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
     S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS, S_CHUNKS,
+    S_TITEMS, S_TGENO, S_TSTATES, S_TCOUNTS, S_TFIRST, S_TRESULTS,
     S_NSLOTS
 };
 
@@ -1202,4 +1204,160 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
         CK(cudaStreamSynchronize(h->stream));
     }
     return MCHB_OK;
+}
+
+// ------------------------------------------------------------------- N1 trace post-processing
+namespace {
+
+int tally_run(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items, int64_t n_items,
+              const int8_t *genotypes, int64_t genotypes_len, int8_t *out_states, int64_t out_states_len,
+              int32_t *out_counts, int32_t *out_first, int64_t tallies_len, mchb_item_result *results) {
+    if (n_items == 0) return MCHB_OK;
+    if (n_items > 0x7fffffff) {
+        h->err = "too many items in one call";
+        return MCHB_ERR_ARGUMENT;
+    }
+    int pn_max = 1, unique_max = 1;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_tally_item &it = items[i];
+        const int64_t pn = (int64_t)it.ploidy * it.n_pos;
+        bool bad = it.n_pos < 0 || it.ploidy < 1 || it.chains < 0 || it.steps < 0 || it.max_unique < 1 ||
+                   it.ploidy > 32 || pn > 16384 || it.max_unique > 8192 || it.genotypes_off < 0 ||
+                   it.genotypes_off + (int64_t)it.chains * it.steps * pn > genotypes_len || it.states_off < 0 ||
+                   it.states_off + (int64_t)it.max_unique * pn > out_states_len || it.tallies_off < 0 ||
+                   it.tallies_off + (int64_t)it.max_unique * it.chains > tallies_len;
+        if (bad) {
+            h->err = "tally item " + std::to_string(i) + " exceeds the given array lengths or the limits "
+                     "(ploidy <= 32, ploidy * n_pos <= 16384, max_unique <= 8192)";
+            return MCHB_ERR_ARGUMENT;
+        }
+        pn_max = std::max<int>(pn_max, (int)pn);
+        unique_max = std::max(unique_max, it.max_unique);
+    }
+    int rc;
+    void *ditems, *dresults, *dcounter;
+    if ((rc = ensure(h, S_TITEMS, sizeof(mchb_tally_item) * (size_t)n_items, &ditems))) return rc;
+    if ((rc = ensure(h, S_TRESULTS, sizeof(mchb_item_result) * (size_t)n_items, &dresults))) return rc;
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8, &dcounter))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_tally_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+    const int8_t *dgeno;
+    int8_t *dstates;
+    int32_t *dcounts, *dfirst;
+    if ((rc = stage_in(h, mem_in, S_TGENO, genotypes, genotypes_len, &dgeno))) return rc;
+    if ((rc = stage_out(h, mem_out, S_TSTATES, out_states, out_states_len, &dstates))) return rc;
+    if ((rc = stage_out(h, mem_out, S_TCOUNTS, out_counts, tallies_len, &dcounts))) return rc;
+    if ((rc = stage_out(h, mem_out, S_TFIRST, out_first, tallies_len, &dfirst))) return rc;
+    // the states array is only written up to n_unique per item: clear the rest for the host
+    if (mem_out == MCHB_MEM_HOST) CK(cudaMemsetAsync(dstates, 0, (size_t)std::max<int64_t>(out_states_len, 1), h->stream));
+    const int tile_bytes = std::max(pn_max, 1024);
+    size_t per_warp = (size_t)unique_max * 4 + (size_t)tile_bytes + 2 * (size_t)pn_max;
+    per_warp = (per_warp + 15) & ~(size_t)15;
+    int warps_per_cta = 4;
+    while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
+    if (per_warp * warps_per_cta > (size_t)h->smem_optin) {
+        h->err = "tally item needs more shared memory than one CTA can have";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const size_t smem = per_warp * warps_per_cta;
+    CK(cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tally_kernel, warps_per_cta * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    TallyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.items = (const mchb_tally_item *)ditems;
+    a.n_items = (int32_t)n_items;
+    a.genotypes = dgeno;
+    a.out_states = dstates;
+    a.out_counts = dcounts;
+    a.out_first = dfirst;
+    a.results = (mchb_item_result *)dresults;
+    a.work_counter = (int32_t *)dcounter;
+    a.smem_per_warp = (int32_t)per_warp;
+    a.pn_max = pn_max;
+    a.tile_bytes = tile_bytes;
+    a.unique_max = unique_max;
+    long long want = (n_items + warps_per_cta - 1) / warps_per_cta;
+    long long grid = std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    tally_kernel<<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+    if (mem_out == MCHB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_states, dstates, (size_t)out_states_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_counts, dcounts, sizeof(int32_t) * (size_t)tallies_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_first, dfirst, sizeof(int32_t) * (size_t)tallies_len, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->kernel_ms += ms;
+    return MCHB_OK;
+}
+
+}  // namespace
+
+extern "C" int mchb_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items,
+                                      int64_t n_items, const int8_t *genotypes, int64_t genotypes_len,
+                                      int8_t *out_states, int64_t out_states_len, int32_t *out_counts,
+                                      int32_t *out_first, int64_t tallies_len, mchb_item_result *results) {
+    if (!h || !items || !results || n_items < 0 || !out_states || !out_counts || !out_first ||
+        (!genotypes && genotypes_len > 0))
+        return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    return tally_run(h, mem_in, mem_out, items, n_items, genotypes, genotypes_len, out_states, out_states_len,
+                     out_counts, out_first, tallies_len, results);
+}
+
+extern "C" int mchb_assemble_tally_batch(mchb_handle *h, const mchb_assemble_params *params,
+                                         const mchb_assemble_item *items, const mchb_tally_item *tally_items,
+                                         int64_t n_items, const double *reads, int64_t reads_len,
+                                         const int64_t *counts, int64_t counts_len, const int8_t *n_alleles,
+                                         int64_t n_alleles_len, const int8_t *initial, int64_t initial_len,
+                                         int64_t genotypes_len, int64_t llks_len, int8_t *out_states,
+                                         int64_t out_states_len, int32_t *out_counts, int32_t *out_first,
+                                         int64_t tallies_len, mchb_item_result *results,
+                                         mchb_item_result *tally_results) {
+    if (!h || !params || !items || !tally_items || !results || !tally_results || n_items < 0 || !out_states ||
+        !out_counts || !out_first || genotypes_len < 0 || llks_len < 0)
+        return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    for (int64_t i = 0; i < n_items; i++) {
+        if (tally_items[i].genotypes_off != items[i].genotypes_off || tally_items[i].n_pos != items[i].n_pos ||
+            tally_items[i].ploidy != items[i].ploidy || tally_items[i].chains != params->chains ||
+            tally_items[i].steps != params->steps) {
+            h->err = "tally item " + std::to_string(i) + " does not describe the trace of assemble item " +
+                     std::to_string(i);
+            return MCHB_ERR_ARGUMENT;
+        }
+    }
+    // inputs to the device, traces in the handle's scratch
+    int rc;
+    const double *dreads;
+    const int64_t *dcounts;
+    const int8_t *dnall, *dinit;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_READS, reads, reads_len, &dreads))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_COUNTS, counts, counts_len, &dcounts))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_NALLELES, n_alleles, n_alleles_len, &dnall))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_INITIAL, initial, initial_len, &dinit))) return rc;
+    void *dog, *dol;
+    if ((rc = ensure(h, S_OUT_G, (size_t)std::max<int64_t>(genotypes_len, 1), &dog))) return rc;
+    if ((rc = ensure(h, S_OUT_L, sizeof(double) * (size_t)std::max<int64_t>(llks_len, 1), &dol))) return rc;
+    rc = mchb_assemble_batch(h, MCHB_MEM_DEVICE, params, items, n_items, dreads, reads_len, dcounts, counts_len, dnall,
+                             n_alleles_len, dinit, initial_len, (int8_t *)dog, genotypes_len, (double *)dol, llks_len,
+                             results);
+    if (rc) return rc;
+    // items that failed in the sampler have no trace worth tallying: zero steps, empty tallies
+    // (kernel_ms and launches keep accumulating: assemble + tally)
+    std::vector<mchb_tally_item> titems(tally_items, tally_items + n_items);
+    for (int64_t i = 0; i < n_items; i++)
+        if (results[i].status != MCHB_ITEM_OK) titems[(size_t)i].steps = 0;
+    return tally_run(h, MCHB_MEM_DEVICE, MCHB_MEM_HOST, titems.data(), n_items, (const int8_t *)dog, genotypes_len,
+                     out_states, out_states_len, out_counts, out_first, tallies_len, tally_results);
 }

@@ -60,3 +60,5 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.ItemResult) == 24
     assert ctypes.sizeof(_lib.LlkItem) == 3 * 8 + 4 * 4
     assert _lib.AssembleItem.inbreeding.offset == 80
+    assert ctypes.sizeof(_lib.TallyItem) == 3 * 8 + 6 * 4
+    assert _lib.TallyItem.max_unique.offset == 44

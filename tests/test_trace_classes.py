@@ -1,0 +1,143 @@
+"""Host-side trace containers against fixtures written by the reference's own
+GenotypeMultiTrace (tests/golden/make_golden_traces.py; mchap/assemble/classes.py:247-376)."""
+import os
+
+import numpy as np
+import pytest
+
+from mchap_b200.assemble.classes import GenotypeMultiTrace, TraceTally
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def fixtures():
+    return np.load(os.path.join(HERE, "golden", "reference_trace_classes.npz"))
+
+
+def case_names(fx):
+    return ["sampled%d" % i for i in range(int(fx["n_sampled"]))] + \
+           ["synthetic%d" % i for i in range(int(fx["n_synthetic"]))]
+
+
+def check_case(fx, name, trace):
+    """trace: GenotypeMultiTrace-like built from the raw trace of case `name`."""
+    np.testing.assert_array_equal(trace.genotypes, fx[name + "_sorted"])
+    burnt = trace.burn(int(fx[name + "_burn"]))
+    post = burnt.posterior()
+    np.testing.assert_array_equal(post.genotypes, fx[name + "_post_genotypes"])
+    np.testing.assert_array_equal(post.probabilities, fx[name + "_post_probs"])
+    mode, prob = post.mode()
+    np.testing.assert_array_equal(mode, fx[name + "_mode"])
+    assert prob == float(fx[name + "_mode_prob"])
+    sup = post.mode_genotype_support()
+    np.testing.assert_array_equal(sup.genotypes, fx[name + "_support_genotypes"])
+    np.testing.assert_array_equal(sup.probabilities, fx[name + "_support_probs"])
+    for c, chain in enumerate(burnt.split()):
+        cp = chain.posterior()
+        np.testing.assert_array_equal(cp.genotypes, fx[name + "_chain%d_genotypes" % c])
+        np.testing.assert_array_equal(cp.probabilities, fx[name + "_chain%d_probs" % c])
+    got = [burnt.replicate_incongruence(threshold=t) for t in (0.6, 0.3, 0.05)]
+    assert got == list(fx[name + "_incongruence"])
+
+
+def test_host_trace_classes_match_reference(fixtures):
+    names = case_names(fixtures)
+    assert len(names) >= 20
+    for name in names:
+        trace = GenotypeMultiTrace(fixtures[name + "_raw"], fixtures[name + "_llks"])
+        np.testing.assert_array_equal(trace.llks, fixtures[name + "_llks"])
+        check_case(fixtures, name, trace)
+
+
+def check_tally(fx, name, tally):
+    """tally: TraceTally of the burnt trace of case `name`."""
+    post = tally.posterior()
+    np.testing.assert_array_equal(post.genotypes, fx[name + "_post_genotypes"])
+    np.testing.assert_array_equal(post.probabilities, fx[name + "_post_probs"])
+    sup = post.mode_genotype_support()
+    np.testing.assert_array_equal(sup.genotypes, fx[name + "_support_genotypes"])
+    np.testing.assert_array_equal(sup.probabilities, fx[name + "_support_probs"])
+    for c, chain in enumerate(tally.split()):
+        cp = chain.posterior()
+        np.testing.assert_array_equal(cp.genotypes, fx[name + "_chain%d_genotypes" % c])
+        np.testing.assert_array_equal(cp.probabilities, fx[name + "_chain%d_probs" % c])
+    got = [tally.replicate_incongruence(threshold=t) for t in (0.6, 0.3, 0.05)]
+    assert got == list(fx[name + "_incongruence"])
+
+
+def test_host_tally_matches_reference(fixtures):
+    for name in case_names(fixtures):
+        trace = GenotypeMultiTrace(fixtures[name + "_raw"], fixtures[name + "_llks"])
+        check_tally(fixtures, name, TraceTally.from_trace(trace.burn(int(fixtures[name + "_burn"]))))
+
+
+@pytest.mark.gpu
+def test_device_tally_matches_reference(fixtures):
+    """mchb_trace_tally_batch on the raw (unsorted) fixture traces, all cases in one call."""
+    import mchap_b200
+    from mchap_b200.api import TALLY_ITEM_DTYPE
+
+    dev = mchap_b200.default_device(0)
+    names = case_names(fixtures)
+    for max_unique in (512, 7):
+        items = np.zeros(len(names), dtype=TALLY_ITEM_DTYPE)
+        raws, go, so, to = [], 0, 0, 0
+        for k, name in enumerate(names):
+            raw = fixtures[name + "_raw"]
+            C, S, P, N = raw.shape
+            items[k] = (go, so, to, N, P, C, S, int(fixtures[name + "_burn"]), max_unique)
+            raws.append(raw.ravel())
+            go += raw.size
+            so += max_unique * P * N
+            to += max_unique * C
+        geno = np.concatenate(raws)
+        states = np.zeros(so, dtype=np.int8)
+        counts = np.zeros(to, dtype=np.int32)
+        first = np.zeros(to, dtype=np.int32)
+        res = dev.trace_tally_call(items, geno, geno.size, states, counts, first)
+        n_over = 0
+        for k, name in enumerate(names):
+            raw = fixtures[name + "_raw"]
+            C, S, P, N = raw.shape
+            want = TraceTally.from_trace(GenotypeMultiTrace(raw, fixtures[name + "_llks"]).burn(int(fixtures[name + "_burn"])))
+            if len(want.states) > max_unique:
+                assert res["status"][k] == 9  # MCHB_ITEM_TALLY_OVERFLOW
+                n_over += 1
+                continue
+            assert res["status"][k] == 0
+            u = int(res["n_het"][k])
+            got = TraceTally(
+                states[items["states_off"][k]:][: u * P * N].reshape(u, P, N),
+                counts[items["tallies_off"][k]:][: u * C].reshape(u, C).astype(np.int64),
+                first[items["tallies_off"][k]:][: u * C].reshape(u, C).astype(np.int64))
+            np.testing.assert_array_equal(got.states, want.states)
+            np.testing.assert_array_equal(got.counts, want.counts)
+            np.testing.assert_array_equal(got.first, want.first)
+            check_tally(fixtures, name, got)
+        assert (n_over > 0) == (max_unique == 7)
+
+
+@pytest.mark.gpu
+def test_fit_posterior_batch_matches_fit_then_host_summaries():
+    """Traces kept on the device + device tallies == traces brought to the host + host classes."""
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.synth import synth_items
+
+    for ploidy, n_pos, depth, max_unique in [(4, 8, 40, 64), (4, 6, 4, 3), (6, 5, 6, 16), (2, 3, 10, 64)]:
+        n_items = 20
+        batch = synth_items(n_items, ploidy=ploidy, n_pos=n_pos, depth=depth, seed=7 * ploidy + n_pos)
+        reads = [batch.item(i)[0] for i in range(n_items)]
+        counts = [batch.item(i)[1] for i in range(n_items)]
+        model = DenovoMCMC(ploidy=ploidy, n_alleles=[2] * n_pos, steps=150, chains=2, random_seed=3)
+        traces = model.fit_batch(reads, counts)
+        tallies = model.fit_posterior_batch(reads, counts, burn=50, max_unique=max_unique)
+        for i in range(n_items):
+            want = TraceTally.from_trace(traces[i].burn(50))
+            np.testing.assert_array_equal(tallies[i].states, want.states, err_msg="item %d" % i)
+            np.testing.assert_array_equal(tallies[i].counts, want.counts)
+            np.testing.assert_array_equal(tallies[i].first, want.first)
+            a, b = tallies[i].posterior(), traces[i].burn(50).posterior()
+            np.testing.assert_array_equal(a.genotypes, b.genotypes)
+            np.testing.assert_array_equal(a.probabilities, b.probabilities)
+            assert tallies[i].replicate_incongruence(0.6) == traces[i].burn(50).replicate_incongruence(0.6)
