@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-call-exact", action="store_true")
+    ap.add_argument("--no-posterior", action="store_true")
     ap.add_argument("--exact-items", type=int, default=50000)
     return ap.parse_args()
 
@@ -339,6 +340,46 @@ def run_b200(args, rank, world):
             "host_chunks": dev.last_host_chunks, "note": "one handle, pinned host buffers: H2D, kernels in chunks of consecutive items, each chunk's trace D2H overlapping the next chunks' kernels",
         }
 
+    # ---- the same workload as the application consumes it (mchap/application/assemble.py:123-170:
+    # fit -> burn -> posterior / incongruence): traces stay in HBM, the tally kernel reduces them,
+    # only the tallies come back
+    posterior = None
+    if rank == 0 and not args.no_e2e and not args.no_posterior:
+        from mchap_b200.api import TALLY_ITEM_DTYPE
+
+        b, items = batches[0]
+        burn, table = 500, 64   # CLI defaults: --mcmc-steps 1500 --mcmc-burn 500
+        titems = np.zeros(len(items), dtype=TALLY_ITEM_DTYPE)
+        titems["genotypes_off"] = items["genotypes_off"]
+        titems["n_pos"], titems["ploidy"] = items["n_pos"], items["ploidy"]
+        titems["chains"], titems["steps"], titems["burn"], titems["max_unique"] = CHAINS, MCMC_STEPS, burn, table
+        titems["states_off"] = np.arange(len(items), dtype=np.int64) * table * PLOIDY * N_POS
+        titems["tallies_off"] = np.arange(len(items), dtype=np.int64) * table * CHAINS
+        o_states = np.zeros(len(items) * table * PLOIDY * N_POS, dtype=np.int8)
+        o_counts = np.zeros(len(items) * table * CHAINS, dtype=np.int32)
+        o_first = np.zeros_like(o_counts)
+
+        def tally_step():
+            return dev.assemble_tally_call(
+                items, titems, params, h_reads.numpy(), h_counts.numpy(), h_nall.numpy(), None,
+                (h_reads.numel(), h_counts.numel(), h_nall.numel(), 0, g_len, l_len), o_states, o_counts, o_first)
+
+        tally_step()
+        t0 = time.perf_counter()
+        n_post = min(K, 3)
+        for _ in range(n_post):
+            _, tres = tally_step()
+        dt = time.perf_counter() - t0
+        posterior = {
+            "value": n_post * items_per_step * CHAINS * MCMC_STEPS / dt, "unit": UNIT, "steps": n_post,
+            "ms_per_step": 1e3 * dt / n_post, "kernel_ms_per_step": dev.last_kernel_ms,
+            "burn": burn, "max_unique": table, "items_over_max_unique": int((tres["status"] != 0).sum()),
+            "mean_unique_genotypes": float(tres["n_het"].mean()),
+            "d2h_bytes_per_step": int(o_states.nbytes + 2 * o_counts.nbytes + 2 * len(items) * 24),
+            "note": "mchb_assemble_tally_batch on this rank: host inputs, traces kept in HBM, tallies of the burnt "
+                    "trace (distinct genotypes, counts and first occurrences per chain) to the host",
+        }
+
     # ---- roofline of the dominant kernel (assemble_kernel): FP64 SIMT pipe
     main_items_per_launch = int(np.mean([(b.n_reads() <= 32).sum() for b, _ in batches]))
     peak_tf = dev.measure_fp64_peak()
@@ -388,7 +429,7 @@ def run_b200(args, rank, world):
                        "l2": "each step reads a different batch and writes a 9.6 GB trace (> L2)",
                        "mean_unique_reads": float(np.mean([b.n_reads().mean() for b, _ in batches]))},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "call_exact": call_exact,
+            "call_exact": call_exact, "e2e_posterior": posterior,
             "wall_ms_per_step": 1e3 * wall_max / K,
         }
         print(json.dumps(line), flush=True)
