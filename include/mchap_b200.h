@@ -46,6 +46,7 @@ extern "C" {
 
 #define MCHB_MEM_HOST 0
 #define MCHB_MEM_DEVICE 1
+#define MCHB_MEM_LAST_TRACE 2  /* mchb_trace_tally_batch only: the trace that the last mchb_assemble_tally_batch left in the handle's scratch */
 
 typedef struct mchb_handle mchb_handle;
 
@@ -267,7 +268,10 @@ typedef struct {
     int32_t burn, max_unique;
 } mchb_tally_item;
 
-/* mem_in: where `genotypes` lives; mem_out: where the three output arrays live. */
+/* mem_in: where `genotypes` lives (MCHB_MEM_LAST_TRACE: `genotypes` is ignored and the offsets
+ * index the trace kept by the last mchb_assemble_tally_batch call on this handle, e.g. to tally
+ * the few items that overflowed max_unique again with a larger table, without sampling again);
+ * mem_out: where the three output arrays live. */
 int mchb_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items,
                            int64_t n_items, const int8_t *genotypes, int64_t genotypes_len,
                            int8_t *out_states, int64_t out_states_len, int32_t *out_counts,

@@ -25,6 +25,7 @@ ITEM_TALLY_OVERFLOW = 9
 
 MEM_HOST = 0
 MEM_DEVICE = 1
+MEM_LAST_TRACE = 2
 
 
 class Limits(C.Structure):

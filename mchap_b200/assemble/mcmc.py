@@ -182,61 +182,70 @@ class DenovoMCMC(object):
         return out
 
     def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None,
-                            n_alleles_list=None, seeds=None, max_unique=64):
+                            n_alleles_list=None, seeds=None, max_unique=128):
         """``fit(...).burn(burn)`` for many items with the traces kept on the device: returns one
         TraceTally per item (``.posterior()``, ``.split()``, ``.replicate_incongruence()`` behave
         like the burnt GenotypeMultiTrace of the reference, mchap/application/assemble.py:123-170).
 
         Only the tallies (distinct genotypes, counts and first occurrences per chain) cross the
-        bus; an item with more than ``max_unique`` distinct genotypes is redone with a table as
-        large as its trace."""
+        bus.  Items with more than ``max_unique`` distinct genotypes are tallied a second time from
+        the trace still held on the device, with a table as large as the trace."""
         dev = self.device or default_device()
         n = len(reads_list)
+        burn = int(burn)
+        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds)
+        items = pk["items"]
+        params, keep = self._params(pk["nmax"])
+        kept = max(self.steps - max(burn, 0), 0) * self.chains
         out = [None] * n
-        todo = list(range(n))
-        table = int(max_unique)
-        kept = max(self.steps - max(int(burn), 0), 0) * self.chains
-        while todo:
-            sub = lambda lst: None if lst is None else [lst[i] for i in todo]
-            pk = self._pack(sub(reads_list), sub(counts_list), sub(initial_list), sub(n_alleles_list), sub(seeds))
-            items = pk["items"]
-            m = len(items)
-            titems = np.zeros(m, dtype=TALLY_ITEM_DTYPE)
-            pn = items["ploidy"].astype(np.int64) * items["n_pos"].astype(np.int64)
-            titems["genotypes_off"] = items["genotypes_off"]
-            titems["n_pos"], titems["ploidy"] = items["n_pos"], items["ploidy"]
-            titems["chains"], titems["steps"], titems["burn"] = self.chains, self.steps, int(burn)
-            titems["max_unique"] = table
-            titems["states_off"] = np.concatenate([[0], np.cumsum(pn * table)[:-1]])
-            titems["tallies_off"] = np.arange(m, dtype=np.int64) * table * self.chains
-            out_states = np.zeros(max(int((pn * table).sum()), 1), dtype=np.int8)
-            out_counts = np.zeros(max(m * table * self.chains, 1), dtype=np.int32)
-            out_first = np.zeros_like(out_counts)
-            params, keep = self._params(pk["nmax"])
-            results, tres = dev.assemble_tally_call(
-                items, titems, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"],
-                pk["lens"] + (pk["genotypes_len"], pk["llks_len"]), out_states, out_counts, out_first)
-            again = []
-            for k, i in enumerate(todo):
-                raise_item_status(int(results["status"][k]), i if n > 1 else None)
+
+        def tally_items(idx, table):
+            t = np.zeros(len(idx), dtype=TALLY_ITEM_DTYPE)
+            pn = items["ploidy"][idx].astype(np.int64) * items["n_pos"][idx].astype(np.int64)
+            t["genotypes_off"] = items["genotypes_off"][idx]
+            t["n_pos"], t["ploidy"] = items["n_pos"][idx], items["ploidy"][idx]
+            t["chains"], t["steps"], t["burn"], t["max_unique"] = self.chains, self.steps, burn, table
+            t["states_off"] = np.concatenate([[0], np.cumsum(pn * table)[:-1]])
+            t["tallies_off"] = np.arange(len(idx), dtype=np.int64) * table * self.chains
+            return (t, np.zeros(max(int((pn * table).sum()), 1), dtype=np.int8),
+                    np.zeros(max(len(idx) * table * self.chains, 1), dtype=np.int32),
+                    np.zeros(max(len(idx) * table * self.chains, 1), dtype=np.int32))
+
+        def collect(idx, t, tres, states, counts, first):
+            over = []
+            for k, i in enumerate(idx):
                 if int(tres["status"][k]) == TALLY_OVERFLOW:
-                    again.append(i)
+                    over.append(i)
                     continue
                 raise_item_status(int(tres["status"][k]), i if n > 1 else None)
                 u = int(tres["n_het"][k])
-                P, N = int(items["ploidy"][k]), int(items["n_pos"][k])
-                so, to = int(titems["states_off"][k]), int(titems["tallies_off"][k])
+                P, N = int(items["ploidy"][i]), int(items["n_pos"][i])
+                so, to = int(t["states_off"][k]), int(t["tallies_off"][k])
                 out[i] = TraceTally(
-                    out_states[so: so + u * P * N].reshape(u, P, N).copy(),
-                    out_counts[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64),
-                    out_first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64))
-            if again and table >= min(kept, 8192):
-                # more distinct genotypes than the device table can hold: tally those on the host
-                traces = self.fit_batch(sub2(reads_list, again), sub2(counts_list, again), sub2(initial_list, again),
-                                        sub2(n_alleles_list, again), sub2(seeds, again))
-                for i, t in zip(again, traces):
-                    out[i] = TraceTally.from_trace(t.burn(int(burn)))
-                again = []
-            todo = again
-            table = max(1, min(kept, 8192))
+                    states[so: so + u * P * N].reshape(u, P, N).copy(),
+                    counts[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64),
+                    first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64))
+            return over
+
+        everything = np.arange(n)
+        table = max(1, min(int(max_unique), max(kept, 1)))
+        t, states, counts, first = tally_items(everything, table)
+        results, tres = dev.assemble_tally_call(
+            items, t, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"],
+            pk["lens"] + (pk["genotypes_len"], pk["llks_len"]), states, counts, first)
+        for i in range(n):
+            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+        over = collect(everything, t, tres, states, counts, first)
+        if over and kept <= 8192:
+            # second look at the same device-resident trace with a table that cannot overflow
+            idx = np.array(over)
+            t, states, counts, first = tally_items(idx, kept)
+            tres = dev.trace_tally_call(t, None, 0, states, counts, first, mem_in=L.MEM_LAST_TRACE)
+            over = collect(idx, t, tres, states, counts, first)
+        if over:
+            # more distinct genotypes than the device table can hold: bring those traces to the host
+            traces = self.fit_batch(sub2(reads_list, over), sub2(counts_list, over), sub2(initial_list, over),
+                                    sub2(n_alleles_list, over), sub2(seeds, over))
+            for i, tr in zip(over, traces):
+                out[i] = TraceTally.from_trace(tr.burn(burn))
         return out

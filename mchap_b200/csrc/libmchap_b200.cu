@@ -42,6 +42,7 @@ struct mchb_handle {
     float kernel_ms = 0.f;
     int32_t launches = 0;
     int32_t host_chunks = 1;
+    int64_t last_trace_len = 0;  // int8 elements of the trace left in scratch by mchb_assemble_tally_batch
     std::vector<DevBuf> bufs;  // scratch slots, grown on demand
 };
 
@@ -550,6 +551,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     if ((rc = stage_in(h, mem, S_COUNTS, counts, counts_len, &dcounts))) return rc;
     if ((rc = stage_in(h, mem, S_NALLELES, n_alleles, n_alleles_len, &dnall))) return rc;
     if ((rc = stage_in(h, mem, S_INITIAL, initial, initial_len, &dinit))) return rc;
+    if (mem == MCHB_MEM_HOST) h->last_trace_len = 0;  // the scratch trace of an earlier tally call is overwritten
     if ((rc = stage_out(h, mem, S_OUT_G, out_genotypes, out_genotypes_len, &dog))) return rc;
     if ((rc = stage_out(h, mem, S_OUT_L, out_llks, out_llks_len, &dol))) return rc;
 
@@ -1305,10 +1307,18 @@ extern "C" int mchb_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, c
                                       int8_t *out_states, int64_t out_states_len, int32_t *out_counts,
                                       int32_t *out_first, int64_t tallies_len, mchb_item_result *results) {
     if (!h || !items || !results || n_items < 0 || !out_states || !out_counts || !out_first ||
-        (!genotypes && genotypes_len > 0))
+        (mem_in != MCHB_MEM_LAST_TRACE && !genotypes && genotypes_len > 0))
         return MCHB_ERR_ARGUMENT;
     begin_call(h);
     CK(cudaSetDevice(h->device));
+    if (mem_in == MCHB_MEM_LAST_TRACE) {
+        if (h->last_trace_len <= 0 || !h->bufs[S_OUT_G].p) {
+            h->err = "no trace of an earlier mchb_assemble_tally_batch call is held by this handle";
+            return MCHB_ERR_ARGUMENT;
+        }
+        return tally_run(h, MCHB_MEM_DEVICE, mem_out, items, n_items, (const int8_t *)h->bufs[S_OUT_G].p,
+                         h->last_trace_len, out_states, out_states_len, out_counts, out_first, tallies_len, results);
+    }
     return tally_run(h, mem_in, mem_out, items, n_items, genotypes, genotypes_len, out_states, out_states_len,
                      out_counts, out_first, tallies_len, results);
 }
@@ -1353,6 +1363,7 @@ extern "C" int mchb_assemble_tally_batch(mchb_handle *h, const mchb_assemble_par
                              n_alleles_len, dinit, initial_len, (int8_t *)dog, genotypes_len, (double *)dol, llks_len,
                              results);
     if (rc) return rc;
+    h->last_trace_len = genotypes_len;
     // items that failed in the sampler have no trace worth tallying: zero steps, empty tallies
     // (kernel_ms and launches keep accumulating: assemble + tally)
     std::vector<mchb_tally_item> titems(tally_items, tally_items + n_items);
