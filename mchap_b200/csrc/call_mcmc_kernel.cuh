@@ -37,6 +37,7 @@ struct CallMcmcArgs {
     int32_t *work_counter;
     int32_t umax, hmax, pmax;
     int32_t smem_per_warp;
+    int32_t memo_off;           // byte offset of the per-warp memo region, -1: no memo
 };
 
 // host-initialised: LOG_RATIO[i * 17 + j] = log((double)i / (double)j), 1 <= i, j <= 16
@@ -68,6 +69,14 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
     int *ord = gs + a.pmax;                                         // [pmax] slot order
     int *ini = ord + a.pmax;                                        // [pmax] initial genotype
     uint32_t *ring = reinterpret_cast<uint32_t *>(ini + a.pmax);    // [128] RNG word ring
+    // Memo: the categorical distribution of slot k is a function of (k, genotype) only, and a
+    // chain that sits in a mode asks for the same one step after step.  Per slot: the genotype it
+    // was computed for, its cumulative sums (what random_choice searches) and the candidates' llks.
+    const bool memo = a.memo_off >= 0;
+    double *mcs = reinterpret_cast<double *>(sm + (memo ? a.memo_off : 0));   // [pmax][hmax] cumulative sums
+    double *mls = mcs + (size_t)a.pmax * a.hmax;                              // [pmax][hmax] llks
+    int *mkey = reinterpret_cast<int *>(mls + (size_t)a.pmax * a.hmax);       // [pmax][pmax] genotype of the entry
+    int *mvalid = mkey + a.pmax * a.pmax;                                     // [pmax]
 
     for (;;) {
         int w = 0;
@@ -87,6 +96,9 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
         ws.init(a.words + (size_t)a.item_stream[item_id] * a.stream_len, a.stream_len, ring, lane);
         long long evals = 0;
         int err = 0;
+        if (memo) {
+            for (int k = lane; k < a.pmax; k += 32) mvalid[k] = 0;
+        }
 
         // ---- raw table t[r][h] (likelihood.py:48-58 per haplotype), counts
         __syncwarp();
@@ -213,6 +225,29 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                 double llk_last = 0.0;
                 for (int jj = 0; jj < P && !err; jj++) {
                     const int k = ord[jj];
+                    if (memo) {
+                        bool same = mvalid[k] != 0;
+                        for (int s = lane; s < P; s += 32) same = same && (mkey[k * P + s] == gs[s]);
+                        if (__all_sync(MCHB_FULL, same)) {
+                            // same draw from the remembered cumulative sums (jitutils.py:77-92)
+                            evals += H;
+                            const double u = ws.next_double();
+                            int choice = 0;
+                            for (int a0 = 0; a0 < H; a0 += 32) {
+                                const int al = a0 + lane;
+                                choice += __popc(__ballot_sync(MCHB_FULL, al < H && mcs[k * H + al] <= u));
+                            }
+                            if (choice >= H) {
+                                err = MCHB_ITEM_CHOICE_RANGE;
+                                break;
+                            }
+                            llk_last = mls[k * H + choice];
+                            __syncwarp();
+                            gs[k] = choice;
+                            __syncwarp();
+                            continue;
+                        }
+                    }
                     const int current = gs[k];
                     int copies_cur = 0;  // mcmc.py:66-68
                     for (int s = 0; s < P; s++) copies_cur += (gs[s] == current);
@@ -332,6 +367,10 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                             if (lane >= m) v += o;
                         }
                         v += carry;
+                        if (memo && al < H) {
+                            mcs[k * H + al] = v;
+                            mls[k * H + al] = ls[al];
+                        }
                         choice += __popc(__ballot_sync(MCHB_FULL, al < H && v <= u));
                         carry = __shfl_sync(MCHB_FULL, v, 31);
                     }
@@ -340,6 +379,11 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                         break;
                     }
                     llk_last = ls[choice];
+                    __syncwarp();
+                    if (memo) {
+                        for (int s = lane; s < P; s += 32) mkey[k * P + s] = gs[s];
+                        if (lane == 0) mvalid[k] = 1;
+                    }
                     __syncwarp();
                     gs[k] = choice;
                     __syncwarp();

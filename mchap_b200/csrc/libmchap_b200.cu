@@ -1103,9 +1103,15 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
         }
         words_needed = std::max(words_needed, (int64_t)pp.chains * pp.steps * (4 * (int64_t)it.ploidy + 8) + 64);
     }
-    const size_t per_warp =
+    size_t per_warp =
         (((size_t)g.umax * g.hmax + g.umax + 2 * (size_t)g.hmax + (size_t)g.hmax * (g.pmax + 2)) * 8 + 3 * (size_t)g.pmax * 4 + 512 + 15) &
         ~(size_t)15;
+    // memo of the conditional distributions (cumulative sums + llks per genotype slot): kept in
+    // shared memory when it is small next to the read x haplotype table
+    const size_t memo_bytes = ((size_t)g.pmax * g.hmax * 16 + (size_t)g.pmax * g.pmax * 4 + (size_t)g.pmax * 4 + 15) & ~(size_t)15;
+    const bool use_memo = memo_bytes <= 16384;
+    const size_t memo_off = per_warp;
+    if (use_memo) per_warp += memo_bytes;
     int warps_per_cta = 4;
     while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
     if (per_warp * warps_per_cta > (size_t)h->smem_optin) {
@@ -1182,6 +1188,7 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
         a.hmax = g.hmax;
         a.pmax = g.pmax;
         a.smem_per_warp = (int32_t)per_warp;
+        a.memo_off = use_memo ? (int32_t)memo_off : -1;
         long long want = ((long long)todo.size() + warps_per_cta - 1) / warps_per_cta;
         long long grid = std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
         call_mcmc_kernel<<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
