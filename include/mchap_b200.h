@@ -293,6 +293,29 @@ int mchb_assemble_tally_batch(mchb_handle *h, const mchb_assemble_params *params
                               int64_t tallies_len, mchb_item_result *results,
                               mchb_item_result *tally_results);
 
+/* The same for calling traces (mchap call): replaces calling/classes.py:178-242
+ * GenotypeAllelesMultiTrace.burn / posterior / split and feeds replicate_incongruence (221-256) and
+ * posterior_frequencies (258-297).  Trace int32[chains, steps, ploidy] at alleles + genotypes_off;
+ * tally items have n_pos == 1 (a "row" is one allele index; the sampler already keeps the alleles
+ * of a step sorted, calling/mcmc.py:325-326); out_states is int32[max_unique, ploidy]. */
+int mchb_call_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items,
+                                int64_t n_items, const int32_t *alleles, int64_t alleles_len,
+                                int32_t *out_states, int64_t out_states_len, int32_t *out_counts,
+                                int32_t *out_first, int64_t tallies_len, mchb_item_result *results);
+
+/* mchb_call_mcmc_batch followed by mchb_call_trace_tally_batch with the trace kept on the device
+ * (HOST inputs and tallies; tally_items[i].genotypes_off must repeat items[i].gl_off): the call
+ * behind `CallingMCMC(...).fit(...).burn(n)` of mchap/application/call.py:134-182 for a batch. */
+int mchb_call_mcmc_tally_batch(mchb_handle *h, const mchb_call_mcmc_params *params,
+                               const mchb_call_item *items, const mchb_tally_item *tally_items,
+                               int64_t n_items, const double *reads, int64_t reads_len,
+                               const int64_t *counts, int64_t counts_len, const int8_t *haplotypes,
+                               int64_t haplotypes_len, const double *freqs, int64_t freqs_len,
+                               const int32_t *initial, int32_t pstride, int64_t alleles_len,
+                               int64_t llks_len, int32_t *out_states, int64_t out_states_len,
+                               int32_t *out_counts, int32_t *out_first, int64_t tallies_len,
+                               mchb_item_result *results, mchb_item_result *tally_results);
+
 #ifdef __cplusplus
 }
 #endif

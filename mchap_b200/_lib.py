@@ -167,7 +167,8 @@ SYMBOLS = [
     "mchb_genotype_rank", "mchb_genotype_unrank", "mchb_log_likelihood_batch",
     "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
-    "mchb_trace_tally_batch", "mchb_assemble_tally_batch",
+    "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
+    "mchb_call_mcmc_tally_batch",
 ]
 
 
@@ -247,6 +248,13 @@ def load():
         L.mchb_assemble_tally_batch.argtypes = [
             vp, C.POINTER(AssembleParams), vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
             vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp,
+        ]
+        L.mchb_call_trace_tally_batch.restype = C.c_int
+        L.mchb_call_trace_tally_batch.argtypes = L.mchb_trace_tally_batch.argtypes
+        L.mchb_call_mcmc_tally_batch.restype = C.c_int
+        L.mchb_call_mcmc_tally_batch.argtypes = [
+            vp, C.POINTER(CallMcmcParams), vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
+            vp, C.c_int64, vp, C.c_int32, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp,
         ]
         _lib = L
         return _lib

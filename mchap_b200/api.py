@@ -232,6 +232,38 @@ class Device:
             _ptr(alleles), a_len, _ptr(llks), l_len, _ptr(results)))
         return dict(alleles=alleles, llks=llks, results=results)
 
+    def call_trace_tally_call(self, items, alleles, alleles_len, out_states, out_counts, out_first,
+                              mem_in=L.MEM_HOST, mem_out=L.MEM_HOST):
+        """Thin wrapper of mchb_call_trace_tally_batch (int32 traces, items with n_pos == 1)."""
+        n = len(items)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        self._check(self._lib.mchb_call_trace_tally_batch(
+            self._h, mem_in, mem_out, _ptr(items), n, _ptr(alleles), int(alleles_len), _ptr(out_states),
+            int(out_states.size), _ptr(out_counts), _ptr(out_first), int(out_counts.size), _ptr(results)))
+        return results
+
+    def call_mcmc_tally(self, batch, tally_items, steps, chains, step_type, out_states, out_counts, out_first,
+                        initial=None, pstride=0):
+        """mchb_call_mcmc_tally_batch: the sampler of call_mcmc with the traces kept on the device and
+        tallied there -> (results, tally_results)."""
+        n = batch.n
+        per = chains * steps
+        a_len = int(per * batch.items["ploidy"].astype(np.int64).sum())
+        l_len = per * n
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        tally_results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        p = L.CallMcmcParams()
+        p.steps, p.chains, p.step_type = int(steps), int(chains), int(step_type)
+        p.replay_words, p.replay_len, p.rng_words_hint = None, 0, 0
+        ini = None if initial is None else np.ascontiguousarray(initial, dtype=np.int32)
+        self._check(self._lib.mchb_call_mcmc_tally_batch(
+            self._h, C.byref(p), _ptr(batch.items), _ptr(tally_items), n, _ptr(batch.reads), batch.reads.size,
+            _ptr(batch.counts), 0 if batch.counts is None else batch.counts.size, _ptr(batch.haps), batch.haps.size,
+            _ptr(batch.freqs), 0 if batch.freqs is None else batch.freqs.size, _ptr(ini), int(pstride),
+            a_len, l_len, _ptr(out_states), int(out_states.size), _ptr(out_counts), _ptr(out_first),
+            int(out_counts.size), _ptr(results), _ptr(tally_results)))
+        return results, tally_results
+
     # ------------------------------------------------------------------ K2
     def assemble_call(self, items, params, reads, counts, n_alleles, initial, out_genotypes, out_llks,
                       lens, mem=L.MEM_HOST, keepalive=()):

@@ -7,10 +7,11 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ..api import CallBatch, count_genotypes, default_device, raise_item_status
+from .. import _lib as L
+from ..api import TALLY_ITEM_DTYPE, CallBatch, count_genotypes, default_device, raise_item_status
 from ..assemble.classes import unique_first_occurrence
 
-__all__ = ["CallingMCMC", "GenotypeAllelesMultiTrace", "PosteriorGenotypeAllelesDistribution"]
+__all__ = ["CallingMCMC", "GenotypeAllelesMultiTrace", "PosteriorGenotypeAllelesDistribution", "AllelesTraceTally"]
 
 
 @dataclass
@@ -88,12 +89,7 @@ class GenotypeAllelesMultiTrace(object):
             yield type(self)(g[None, ...], l[None, ...], self.n_allele)
 
     def replicate_incongruence(self, threshold=0.6):
-        modes = [chain.posterior().mode(genotype_support=True) for chain in self.split()]
-        alleles = [m[0] for m in modes if m[-1] >= threshold]
-        if len({a.tobytes() for a in alleles}) <= 1:
-            return 0
-        ploidy = len(alleles[0])
-        return 2 if len(set(np.array(alleles).ravel())) > ploidy else 1
+        return _alleles_incongruence([chain.posterior() for chain in self.split()], threshold)
 
     def posterior_frequencies(self):
         """(frequencies, counts, occurrence) over all recorded steps (classes.py:258-297)."""
@@ -106,6 +102,78 @@ class GenotypeAllelesMultiTrace(object):
             first = np.array([[a not in row[:i] for i, a in enumerate(row)] for row in g])
         occurrence = np.bincount(g[first], minlength=self.n_allele).astype(np.float64)
         n_obs = n_chain * n_step
+        counts /= n_obs
+        occurrence /= n_obs
+        return counts / ploidy, counts, occurrence
+
+
+def _alleles_incongruence(chain_posteriors, threshold):
+    """calling/classes.py:221-256 of the reference on the per-chain posteriors."""
+    modes = [p.mode(genotype_support=True) for p in chain_posteriors]
+    alleles = [m[0] for m in modes if m[-1] >= threshold]
+    if len({a.tobytes() for a in alleles}) <= 1:
+        return 0
+    ploidy = len(alleles[0])
+    return 2 if len(set(np.array(alleles).ravel())) > ploidy else 1
+
+
+@dataclass
+class AllelesTraceTally(object):
+    """What a burnt GenotypeAllelesMultiTrace is reduced to before its summaries are taken,
+    computed on the device by mchb_call_trace_tally_batch: distinct genotypes in order of first
+    occurrence in the chain-major flattened trace, occurrences and first step per chain.
+    The methods return what the same methods of the burnt trace return (reference:
+    mchap/calling/classes.py:147-297)."""
+
+    states: np.ndarray   # int[n_unique, ploidy]
+    counts: np.ndarray   # int64[n_unique, n_chains]
+    first: np.ndarray    # int64[n_unique, n_chains]
+    n_allele: int
+
+    @classmethod
+    def from_trace(cls, trace):
+        n_chain, n_step, ploidy = trace.genotypes.shape
+        flat = trace.genotypes.reshape(n_chain * n_step, ploidy)
+        states, _, _, labels = unique_first_occurrence(flat)
+        labels = labels.reshape(n_chain, n_step)
+        counts = np.zeros((len(states), n_chain), dtype=np.int64)
+        first = np.full((len(states), n_chain), -1, dtype=np.int64)
+        for c in range(n_chain):
+            u, idx, cnt = np.unique(labels[c], return_index=True, return_counts=True)
+            counts[u, c] = cnt
+            first[u, c] = idx
+        return cls(np.array(states), counts, first, trace.n_allele)
+
+    def relabel(self, labels):
+        labels = np.asarray(labels)
+        return type(self)(labels[self.states], self.counts, self.first, labels.max() + 1)
+
+    def posterior(self):
+        totals = self.counts.sum(axis=1)
+        probs = totals / np.sum(totals)
+        idx = np.flip(np.argsort(probs))
+        return PosteriorGenotypeAllelesDistribution(self.states[idx], probs[idx])
+
+    def split(self):
+        for c in range(self.counts.shape[1]):
+            seen = np.flatnonzero(self.counts[:, c] > 0)
+            seen = seen[np.argsort(self.first[seen, c], kind="stable")]
+            yield type(self)(self.states[seen], self.counts[seen, c:c + 1], self.first[seen, c:c + 1], self.n_allele)
+
+    def replicate_incongruence(self, threshold=0.6):
+        return _alleles_incongruence([t.posterior() for t in self.split()], threshold)
+
+    def posterior_frequencies(self):
+        """(frequencies, counts, occurrence): the reference adds 1.0 per recorded allele copy
+        (classes.py:277-297); the sums are integers below 2^53, so adding whole tallies is exact."""
+        totals = self.counts.sum(axis=1)
+        ploidy = self.states.shape[1]
+        counts = np.zeros(self.n_allele)
+        occurrence = np.zeros(self.n_allele)
+        for gen, t in zip(self.states, totals):
+            np.add.at(counts, gen, float(t))
+            occurrence[np.unique(gen)] += float(t)
+        n_obs = np.sum(totals)
         counts /= n_obs
         occurrence /= n_obs
         return counts / ploidy, counts, occurrence
@@ -179,3 +247,78 @@ class CallingMCMC(object):
         if return_results:
             return res, out["results"]
         return res
+
+    def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None, haplotypes_list=None,
+                            priors=None, seeds=None, max_unique=128):
+        """``fit(...).burn(burn)`` for many items with the traces kept on the device: one
+        AllelesTraceTally per item (mchap/application/call.py:134-182 consumes exactly its methods)."""
+        dev = self.device or default_device()
+        n = len(reads_list)
+        st = self._step_type()
+        burn = int(burn)
+        haps = [self.haplotypes] * n if haplotypes_list is None else haplotypes_list
+        prs = ([self.prior] * n if self.prior is not None else None) if priors is None else priors
+        batch = CallBatch(reads_list, haps, self.ploidy, counts_list, prs)
+        seed0 = int(self.random_seed) & 0xFFFFFFFF if self.random_seed is not None else int(
+            np.random.randint(0, 2 ** 32, dtype=np.uint64))
+        items = batch.items
+        P = self.ploidy
+        per = self.chains * self.steps
+        idx = np.arange(n, dtype=np.int64)
+        items["gl_off"] = idx * per * P
+        items["hap_out_off"] = idx * per
+        sd = np.full(n, seed0, dtype=np.uint32) if seeds is None else np.asarray(seeds, dtype=np.uint64).astype(np.uint32)
+        items["reserved"] = sd.view(np.int32)
+        init = None
+        if initial_list is not None and any(i is not None for i in initial_list):
+            init = np.full((n, P), -1, dtype=np.int32)
+            for i, v in enumerate(initial_list):
+                if v is not None:
+                    init[i] = np.asarray(v, dtype=np.int32)
+        kept = max(self.steps - max(burn, 0), 0) * self.chains
+        out = [None] * n
+
+        def tally_items(sel, table):
+            t = np.zeros(len(sel), dtype=TALLY_ITEM_DTYPE)
+            t["genotypes_off"] = items["gl_off"][sel]
+            t["n_pos"], t["ploidy"] = 1, P
+            t["chains"], t["steps"], t["burn"], t["max_unique"] = self.chains, self.steps, burn, table
+            t["states_off"] = np.arange(len(sel), dtype=np.int64) * table * P
+            t["tallies_off"] = np.arange(len(sel), dtype=np.int64) * table * self.chains
+            return (t, np.zeros(max(len(sel) * table * P, 1), dtype=np.int32),
+                    np.zeros(max(len(sel) * table * self.chains, 1), dtype=np.int32),
+                    np.zeros(max(len(sel) * table * self.chains, 1), dtype=np.int32))
+
+        def collect(sel, t, tres, states, counts, first):
+            over = []
+            for k, i in enumerate(sel):
+                if int(tres["status"][k]) == L.ITEM_TALLY_OVERFLOW:
+                    over.append(i)
+                    continue
+                raise_item_status(int(tres["status"][k]), i if n > 1 else None)
+                u = int(tres["n_het"][k])
+                so, to = int(t["states_off"][k]), int(t["tallies_off"][k])
+                out[i] = AllelesTraceTally(
+                    states[so: so + u * P].reshape(u, P).copy(),
+                    counts[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64),
+                    first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64), len(haps[i]))
+            return over
+
+        table = max(1, min(int(max_unique), max(kept, 1)))
+        t, states, counts, first = tally_items(idx, table)
+        results, tres = dev.call_mcmc_tally(batch, t, self.steps, self.chains, st, states, counts, first, init, P)
+        for i in range(n):
+            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+        over = collect(idx, t, tres, states, counts, first)
+        if over and kept <= 8192:
+            sel = np.array(over)
+            t, states, counts, first = tally_items(sel, kept)
+            tres = dev.call_trace_tally_call(t, None, 0, states, counts, first, mem_in=L.MEM_LAST_TRACE)
+            over = collect(sel, t, tres, states, counts, first)
+        if over:
+            pick = lambda lst: None if lst is None else [lst[i] for i in over]
+            traces = self.fit_batch(pick(reads_list), pick(counts_list), pick(initial_list), [haps[i] for i in over],
+                                    pick(prs), pick(seeds))
+            for i, tr in zip(over, traces):
+                out[i] = AllelesTraceTally.from_trace(tr.burn(burn))
+        return out

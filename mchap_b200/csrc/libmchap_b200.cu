@@ -43,6 +43,7 @@ struct mchb_handle {
     int32_t launches = 0;
     int32_t host_chunks = 1;
     int64_t last_trace_len = 0;  // int8 elements of the trace left in scratch by mchb_assemble_tally_batch
+    int64_t last_call_trace_len = 0;  // int32 elements left by mchb_call_mcmc_tally_batch
     std::vector<DevBuf> bufs;  // scratch slots, grown on demand
 };
 
@@ -1139,6 +1140,7 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
     if ((rc = stage_in(h, mem, S_HAPS, haplotypes, haplotypes_len, &dhaps))) return rc;
     if ((rc = stage_in(h, mem, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
     if ((rc = stage_in(h, mem, S_INIT32, initial, initial ? n_items * pstride : 0, &dinit))) return rc;
+    if (mem == MCHB_MEM_HOST) h->last_call_trace_len = 0;  // the scratch trace of an earlier tally call is overwritten
     if ((rc = stage_out(h, mem, S_OUT_A32, out_alleles, out_alleles_len, &doa))) return rc;
     if ((rc = stage_out(h, mem, S_OUT_L, out_llks, out_llks_len, &dol))) return rc;
     CK(cudaFuncSetAttribute(call_mcmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1218,7 +1220,8 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
 // ------------------------------------------------------------------- N1 trace post-processing
 namespace {
 
-int tally_run(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items, int64_t n_items,
+// elem_size 1: int8 assembly traces; 4: int32 calling traces.  Lengths and offsets are in elements.
+int tally_run(mchb_handle *h, int elem_size, int mem_in, int mem_out, const mchb_tally_item *items, int64_t n_items,
               const int8_t *genotypes, int64_t genotypes_len, int8_t *out_states, int64_t out_states_len,
               int32_t *out_counts, int32_t *out_first, int64_t tallies_len, mchb_item_result *results) {
     if (n_items == 0) return MCHB_OK;
@@ -1240,7 +1243,7 @@ int tally_run(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *it
                      "(ploidy <= 32, ploidy * n_pos <= 16384, max_unique <= 8192)";
             return MCHB_ERR_ARGUMENT;
         }
-        pn_max = std::max<int>(pn_max, (int)pn);
+        pn_max = std::max<int>(pn_max, (int)pn * elem_size);  // bytes
         unique_max = std::max(unique_max, it.max_unique);
     }
     int rc;
@@ -1253,12 +1256,13 @@ int tally_run(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *it
     const int8_t *dgeno;
     int8_t *dstates;
     int32_t *dcounts, *dfirst;
-    if ((rc = stage_in(h, mem_in, S_TGENO, genotypes, genotypes_len, &dgeno))) return rc;
-    if ((rc = stage_out(h, mem_out, S_TSTATES, out_states, out_states_len, &dstates))) return rc;
+    if ((rc = stage_in(h, mem_in, S_TGENO, genotypes, genotypes_len * elem_size, &dgeno))) return rc;
+    if ((rc = stage_out(h, mem_out, S_TSTATES, out_states, out_states_len * elem_size, &dstates))) return rc;
     if ((rc = stage_out(h, mem_out, S_TCOUNTS, out_counts, tallies_len, &dcounts))) return rc;
     if ((rc = stage_out(h, mem_out, S_TFIRST, out_first, tallies_len, &dfirst))) return rc;
     // the states array is only written up to n_unique per item: clear the rest for the host
-    if (mem_out == MCHB_MEM_HOST) CK(cudaMemsetAsync(dstates, 0, (size_t)std::max<int64_t>(out_states_len, 1), h->stream));
+    if (mem_out == MCHB_MEM_HOST)
+        CK(cudaMemsetAsync(dstates, 0, (size_t)std::max<int64_t>(out_states_len * elem_size, 1), h->stream));
     const int tile_bytes = std::max(pn_max, 1024);
     size_t per_warp = (size_t)unique_max * 4 + (size_t)tile_bytes + 2 * (size_t)pn_max;
     per_warp = (per_warp + 15) & ~(size_t)15;
@@ -1269,9 +1273,14 @@ int tally_run(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *it
         return MCHB_ERR_ARGUMENT;
     }
     const size_t smem = per_warp * warps_per_cta;
-    CK(cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tally_kernel, warps_per_cta * 32, smem));
+    if (elem_size == 1) {
+        CK(cudaFuncSetAttribute(tally_kernel<int8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tally_kernel<int8_t>, warps_per_cta * 32, smem));
+    } else {
+        CK(cudaFuncSetAttribute(tally_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, tally_kernel<int32_t>, warps_per_cta * 32, smem));
+    }
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     TallyArgs a;
     memset(&a, 0, sizeof(a));
@@ -1290,13 +1299,14 @@ int tally_run(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *it
     long long want = (n_items + warps_per_cta - 1) / warps_per_cta;
     long long grid = std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
     CK(cudaEventRecord(h->ev0, h->stream));
-    tally_kernel<<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
+    if (elem_size == 1) tally_kernel<int8_t><<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
+    else tally_kernel<int32_t><<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
     CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
     if (mem_out == MCHB_MEM_HOST) {
-        CK(cudaMemcpyAsync(out_states, dstates, (size_t)out_states_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_states, dstates, (size_t)out_states_len * elem_size, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(out_counts, dcounts, sizeof(int32_t) * (size_t)tallies_len, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(out_first, dfirst, sizeof(int32_t) * (size_t)tallies_len, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -1323,10 +1333,10 @@ extern "C" int mchb_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, c
             h->err = "no trace of an earlier mchb_assemble_tally_batch call is held by this handle";
             return MCHB_ERR_ARGUMENT;
         }
-        return tally_run(h, MCHB_MEM_DEVICE, mem_out, items, n_items, (const int8_t *)h->bufs[S_OUT_G].p,
+        return tally_run(h, 1, MCHB_MEM_DEVICE, mem_out, items, n_items, (const int8_t *)h->bufs[S_OUT_G].p,
                          h->last_trace_len, out_states, out_states_len, out_counts, out_first, tallies_len, results);
     }
-    return tally_run(h, mem_in, mem_out, items, n_items, genotypes, genotypes_len, out_states, out_states_len,
+    return tally_run(h, 1, mem_in, mem_out, items, n_items, genotypes, genotypes_len, out_states, out_states_len,
                      out_counts, out_first, tallies_len, results);
 }
 
@@ -1376,6 +1386,81 @@ extern "C" int mchb_assemble_tally_batch(mchb_handle *h, const mchb_assemble_par
     std::vector<mchb_tally_item> titems(tally_items, tally_items + n_items);
     for (int64_t i = 0; i < n_items; i++)
         if (results[i].status != MCHB_ITEM_OK) titems[(size_t)i].steps = 0;
-    return tally_run(h, MCHB_MEM_DEVICE, MCHB_MEM_HOST, titems.data(), n_items, (const int8_t *)dog, genotypes_len,
+    return tally_run(h, 1, MCHB_MEM_DEVICE, MCHB_MEM_HOST, titems.data(), n_items, (const int8_t *)dog, genotypes_len,
                      out_states, out_states_len, out_counts, out_first, tallies_len, tally_results);
+}
+
+extern "C" int mchb_call_trace_tally_batch(mchb_handle *h, int mem_in, int mem_out, const mchb_tally_item *items,
+                                           int64_t n_items, const int32_t *alleles, int64_t alleles_len,
+                                           int32_t *out_states, int64_t out_states_len, int32_t *out_counts,
+                                           int32_t *out_first, int64_t tallies_len, mchb_item_result *results) {
+    if (!h || !items || !results || n_items < 0 || !out_states || !out_counts || !out_first ||
+        (mem_in != MCHB_MEM_LAST_TRACE && !alleles && alleles_len > 0))
+        return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    for (int64_t i = 0; i < n_items; i++)
+        if (items[i].n_pos != 1) {
+            h->err = "calling-trace tally items must have n_pos == 1 (one allele index per genotype slot)";
+            return MCHB_ERR_ARGUMENT;
+        }
+    if (mem_in == MCHB_MEM_LAST_TRACE) {
+        if (h->last_call_trace_len <= 0 || !h->bufs[S_OUT_A32].p) {
+            h->err = "no trace of an earlier mchb_call_mcmc_tally_batch call is held by this handle";
+            return MCHB_ERR_ARGUMENT;
+        }
+        return tally_run(h, 4, MCHB_MEM_DEVICE, mem_out, items, n_items, (const int8_t *)h->bufs[S_OUT_A32].p,
+                         h->last_call_trace_len, (int8_t *)out_states, out_states_len, out_counts, out_first,
+                         tallies_len, results);
+    }
+    return tally_run(h, 4, mem_in, mem_out, items, n_items, (const int8_t *)alleles, alleles_len, (int8_t *)out_states,
+                     out_states_len, out_counts, out_first, tallies_len, results);
+}
+
+extern "C" int mchb_call_mcmc_tally_batch(mchb_handle *h, const mchb_call_mcmc_params *params,
+                                          const mchb_call_item *items, const mchb_tally_item *tally_items,
+                                          int64_t n_items, const double *reads, int64_t reads_len,
+                                          const int64_t *counts, int64_t counts_len, const int8_t *haplotypes,
+                                          int64_t haplotypes_len, const double *freqs, int64_t freqs_len,
+                                          const int32_t *initial, int32_t pstride, int64_t alleles_len,
+                                          int64_t llks_len, int32_t *out_states, int64_t out_states_len,
+                                          int32_t *out_counts, int32_t *out_first, int64_t tallies_len,
+                                          mchb_item_result *results, mchb_item_result *tally_results) {
+    if (!h || !params || !items || !tally_items || !results || !tally_results || n_items < 0 || !out_states ||
+        !out_counts || !out_first || alleles_len < 0 || llks_len < 0)
+        return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    for (int64_t i = 0; i < n_items; i++) {
+        if (tally_items[i].genotypes_off != items[i].gl_off || tally_items[i].n_pos != 1 ||
+            tally_items[i].ploidy != items[i].ploidy || tally_items[i].chains != params->chains ||
+            tally_items[i].steps != params->steps) {
+            h->err = "tally item " + std::to_string(i) + " does not describe the trace of call item " + std::to_string(i);
+            return MCHB_ERR_ARGUMENT;
+        }
+    }
+    int rc;
+    const double *dreads, *dfreqs;
+    const int64_t *dcounts;
+    const int8_t *dhaps;
+    const int32_t *dinit;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_READS, reads, reads_len, &dreads))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_COUNTS, counts, counts_len, &dcounts))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_HAPS, haplotypes, haplotypes_len, &dhaps))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_INIT32, initial, initial ? n_items * pstride : 0, &dinit))) return rc;
+    void *doa, *dol;
+    if ((rc = ensure(h, S_OUT_A32, sizeof(int32_t) * (size_t)std::max<int64_t>(alleles_len, 1), &doa))) return rc;
+    if ((rc = ensure(h, S_OUT_L, sizeof(double) * (size_t)std::max<int64_t>(llks_len, 1), &dol))) return rc;
+    rc = mchb_call_mcmc_batch(h, MCHB_MEM_DEVICE, params, items, n_items, dreads, reads_len, dcounts, counts_len, dhaps,
+                              haplotypes_len, dfreqs, freqs_len, dinit, pstride, (int32_t *)doa, alleles_len,
+                              (double *)dol, llks_len, results);
+    if (rc) return rc;
+    h->last_call_trace_len = alleles_len;
+    std::vector<mchb_tally_item> titems(tally_items, tally_items + n_items);
+    for (int64_t i = 0; i < n_items; i++)
+        if (results[i].status != MCHB_ITEM_OK) titems[(size_t)i].steps = 0;
+    return tally_run(h, 4, MCHB_MEM_DEVICE, MCHB_MEM_HOST, titems.data(), n_items, (const int8_t *)doa, alleles_len,
+                     (int8_t *)out_states, out_states_len, out_counts, out_first, tallies_len, tally_results);
 }

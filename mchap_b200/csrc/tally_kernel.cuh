@@ -20,7 +20,7 @@ namespace mchb {
 struct TallyArgs {
     const mchb_tally_item *items;
     int32_t n_items;
-    const int8_t *genotypes;
+    const int8_t *genotypes;  // elements of ES bytes (ES = template parameter of the kernel)
     int8_t *out_states;
     int32_t *out_counts;
     int32_t *out_first;
@@ -32,17 +32,22 @@ struct TallyArgs {
     int32_t unique_max;      // largest max_unique of the batch
 };
 
-// signed-byte lexicographic order of two rows of n bytes in shared memory
-__device__ __forceinline__ int row_compare(const int8_t *x, const int8_t *y, int n) {
+// lexicographic order of two rows of n signed elements in shared memory
+template <typename T>
+__device__ __forceinline__ int row_compare(const T *x, const T *y, int n) {
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
-        const int d = (int)x[j] - (int)y[j];
-        if (d) return d;
+        const T xv = x[j], yv = y[j];
+        if (xv != yv) return xv < yv ? -1 : 1;
     }
     return 0;
 }
 
+// T = int8_t: assembly traces int8[chains, steps, ploidy, n_pos]; T = int32_t: calling traces
+// int32[chains, steps, ploidy] (n_pos = 1: a row is one allele index)
+template <typename T>
 __global__ void __launch_bounds__(128) tally_kernel(const __grid_constant__ TallyArgs a) {
+    constexpr int ES = (int)sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -59,11 +64,12 @@ __global__ void __launch_bounds__(128) tally_kernel(const __grid_constant__ Tall
         if (w >= a.n_items) break;
         const mchb_tally_item it = a.items[w];
         const int P = it.ploidy, N = it.n_pos, C = it.chains, S = it.steps;
-        const int PN = P * N;
+        const int PN = P * N * ES;   // bytes of one recorded genotype
+        const int NB = N * ES;       // bytes of one row
         const int burn = min(max(it.burn, 0), S);
         const int U = it.max_unique;
-        const int8_t *g = a.genotypes + it.genotypes_off;
-        int8_t *states = a.out_states + it.states_off;
+        const int8_t *g = a.genotypes + it.genotypes_off * ES;
+        int8_t *states = a.out_states + it.states_off * ES;
         int32_t *counts = a.out_counts + it.tallies_off;
         int32_t *first = a.out_first + it.tallies_off;
         for (int i = lane; i < U * C; i += 32) {
@@ -104,10 +110,11 @@ __global__ void __launch_bounds__(128) tally_kernel(const __grid_constant__ Tall
                         int rank = 0;
 #pragma unroll 1
                         for (int k = 0; k < P; k++) {
-                            const int d = row_compare(prev + k * N, prev + lane * N, N);
+                            const int d = row_compare<T>(reinterpret_cast<const T *>(prev + k * NB),
+                                                         reinterpret_cast<const T *>(prev + lane * NB), N);
                             rank += (d < 0) || (d == 0 && k < lane);
                         }
-                        for (int j = 0; j < N; j++) sorted[rank * N + j] = prev[lane * N + j];
+                        for (int j = 0; j < NB; j++) sorted[rank * NB + j] = prev[lane * NB + j];
                     }
                     __syncwarp();
                     uint32_t hsh = 0;

@@ -29,6 +29,7 @@ import numpy as np  # noqa: E402
 import mchap  # noqa: E402
 from mchap.assemble.mcmc import DenovoMCMC  # noqa: E402
 from mchap.assemble.classes import GenotypeMultiTrace  # noqa: E402
+from mchap.calling.classes import GenotypeAllelesMultiTrace  # noqa: E402
 
 from mchap_b200.synth import synth_items  # noqa: E402
 
@@ -109,9 +110,62 @@ def synthetic_cases():
     OUT["n_synthetic"] = np.int64(k)
 
 
+def calling_cases():
+    """Calling traces int[C,S,P] (alleles sorted per step like calling/mcmc.py:325-326 leaves them):
+    GenotypeAllelesMultiTrace.burn / posterior / mode(genotype_support) / split /
+    replicate_incongruence / posterior_frequencies / relabel (calling/classes.py:147-297)."""
+    k = 0
+    for ploidy, n_allele, n_states, steps, chains, seed in [
+        (4, 8, 3, 60, 2, 11), (4, 32, 6, 120, 2, 12), (2, 5, 4, 50, 3, 13), (6, 16, 12, 150, 2, 14),
+        (4, 200, 5, 80, 2, 15), (4, 6, 30, 90, 2, 16), (8, 10, 4, 40, 2, 17), (1, 4, 3, 30, 2, 18),
+    ]:
+        rng = np.random.default_rng(seed)
+        states = np.sort(rng.integers(0, n_allele, size=(n_states, ploidy)), axis=1)
+        gen = np.zeros((chains, steps, ploidy), dtype=np.int64)
+        for c in range(chains):
+            cur = int(rng.integers(n_states))
+            for s in range(steps):
+                if rng.random() < 0.3:
+                    cur = int(rng.integers(n_states)) if rng.random() < 0.5 else (c % n_states)
+                gen[c, s] = states[cur]
+        llks = rng.normal(size=(chains, steps))
+        burn = int(rng.integers(0, steps // 3))
+        name = "calling%d" % k
+        trace = GenotypeAllelesMultiTrace(gen, llks, n_allele)
+        OUT[name + "_genotypes"] = gen.astype(np.int32)
+        OUT[name + "_llks"] = llks
+        OUT[name + "_n_allele"] = np.int64(n_allele)
+        OUT[name + "_burn"] = np.int64(burn)
+        burnt = trace.burn(burn)
+        post = burnt.posterior()
+        OUT[name + "_post_genotypes"] = post.genotypes.astype(np.int64)
+        OUT[name + "_post_probs"] = post.probabilities
+        alleles, gp, sp = post.mode(genotype_support=True)
+        OUT[name + "_mode"] = np.asarray(alleles, dtype=np.int64)
+        OUT[name + "_mode_probs"] = np.array([gp, sp], dtype=np.float64)
+        for c, chain in enumerate(burnt.split()):
+            cp = chain.posterior()
+            OUT[name + "_chain%d_genotypes" % c] = cp.genotypes.astype(np.int64)
+            OUT[name + "_chain%d_probs" % c] = cp.probabilities
+        OUT[name + "_incongruence"] = np.array(
+            [burnt.replicate_incongruence(threshold=t) for t in (0.6, 0.3, 0.05)], dtype=np.int64)
+        fr, cn, oc = burnt.posterior_frequencies()
+        OUT[name + "_freqs"] = np.stack([fr, cn, oc])
+        labels = np.sort(rng.choice(3 * n_allele, size=n_allele, replace=False))
+        rel = burnt.relabel(labels)
+        OUT[name + "_labels"] = labels.astype(np.int64)
+        rp = rel.posterior()
+        OUT[name + "_relabel_post_genotypes"] = rp.genotypes.astype(np.int64)
+        OUT[name + "_relabel_post_probs"] = rp.probabilities
+        OUT[name + "_relabel_freqs"] = np.stack(rel.posterior_frequencies())
+        k += 1
+    OUT["n_calling"] = np.int64(k)
+
+
 if __name__ == "__main__":
     sampled_cases()
     synthetic_cases()
+    calling_cases()
     path = os.path.join(HERE, "reference_trace_classes.npz")
     np.savez_compressed(path, **OUT)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(OUT), os.path.getsize(path) / 1024))

@@ -141,3 +141,115 @@ def test_fit_posterior_batch_matches_fit_then_host_summaries():
             np.testing.assert_array_equal(a.genotypes, b.genotypes)
             np.testing.assert_array_equal(a.probabilities, b.probabilities)
             assert tallies[i].replicate_incongruence(0.6) == traces[i].burn(50).replicate_incongruence(0.6)
+
+
+# ----------------------------------------------------------------------------- calling traces
+def calling_names(fx):
+    return ["calling%d" % i for i in range(int(fx["n_calling"]))]
+
+
+def check_calling(fx, name, burnt):
+    """burnt: GenotypeAllelesMultiTrace or AllelesTraceTally of the burnt trace of case `name`."""
+    post = burnt.posterior()
+    np.testing.assert_array_equal(post.genotypes, fx[name + "_post_genotypes"])
+    np.testing.assert_array_equal(post.probabilities, fx[name + "_post_probs"])
+    alleles, gp, sp = post.mode(genotype_support=True)
+    np.testing.assert_array_equal(alleles, fx[name + "_mode"])
+    assert [gp, sp] == list(fx[name + "_mode_probs"])
+    for c, chain in enumerate(burnt.split()):
+        cp = chain.posterior()
+        np.testing.assert_array_equal(cp.genotypes, fx[name + "_chain%d_genotypes" % c])
+        np.testing.assert_array_equal(cp.probabilities, fx[name + "_chain%d_probs" % c])
+    got = [burnt.replicate_incongruence(threshold=t) for t in (0.6, 0.3, 0.05)]
+    assert got == list(fx[name + "_incongruence"])
+    np.testing.assert_array_equal(np.stack(burnt.posterior_frequencies()), fx[name + "_freqs"])
+    rel = burnt.relabel(fx[name + "_labels"])
+    rp = rel.posterior()
+    np.testing.assert_array_equal(rp.genotypes, fx[name + "_relabel_post_genotypes"])
+    np.testing.assert_array_equal(rp.probabilities, fx[name + "_relabel_post_probs"])
+    np.testing.assert_array_equal(np.stack(rel.posterior_frequencies()), fx[name + "_relabel_freqs"])
+
+
+def test_host_calling_classes_match_reference(fixtures):
+    from mchap_b200.calling.classes import AllelesTraceTally, GenotypeAllelesMultiTrace
+
+    names = calling_names(fixtures)
+    assert len(names) >= 8
+    for name in names:
+        trace = GenotypeAllelesMultiTrace(fixtures[name + "_genotypes"].astype(np.int64), fixtures[name + "_llks"],
+                                          int(fixtures[name + "_n_allele"]))
+        burnt = trace.burn(int(fixtures[name + "_burn"]))
+        check_calling(fixtures, name, burnt)
+        check_calling(fixtures, name, AllelesTraceTally.from_trace(burnt))
+
+
+@pytest.mark.gpu
+def test_device_calling_tally_matches_reference(fixtures):
+    import mchap_b200
+    from mchap_b200.api import TALLY_ITEM_DTYPE
+    from mchap_b200.calling.classes import AllelesTraceTally, GenotypeAllelesMultiTrace
+
+    dev = mchap_b200.default_device(0)
+    names = calling_names(fixtures)
+    max_unique = 64
+    items = np.zeros(len(names), dtype=TALLY_ITEM_DTYPE)
+    gens, go, so, to = [], 0, 0, 0
+    for k, name in enumerate(names):
+        g = fixtures[name + "_genotypes"]
+        C, S, P = g.shape
+        items[k] = (go, so, to, 1, P, C, S, int(fixtures[name + "_burn"]), max_unique)
+        gens.append(g.ravel())
+        go += g.size
+        so += max_unique * P
+        to += max_unique * C
+    alleles = np.concatenate(gens).astype(np.int32)
+    states = np.zeros(so, dtype=np.int32)
+    counts = np.zeros(to, dtype=np.int32)
+    first = np.zeros(to, dtype=np.int32)
+    res = dev.call_trace_tally_call(items, alleles, alleles.size, states, counts, first)
+    for k, name in enumerate(names):
+        g = fixtures[name + "_genotypes"]
+        C, S, P = g.shape
+        assert res["status"][k] == 0
+        u = int(res["n_het"][k])
+        got = AllelesTraceTally(
+            states[items["states_off"][k]:][: u * P].reshape(u, P).astype(np.int64),
+            counts[items["tallies_off"][k]:][: u * C].reshape(u, C).astype(np.int64),
+            first[items["tallies_off"][k]:][: u * C].reshape(u, C).astype(np.int64), int(fixtures[name + "_n_allele"]))
+        want = AllelesTraceTally.from_trace(
+            GenotypeAllelesMultiTrace(g.astype(np.int64), fixtures[name + "_llks"],
+                                      int(fixtures[name + "_n_allele"])).burn(int(fixtures[name + "_burn"])))
+        np.testing.assert_array_equal(got.states, want.states)
+        np.testing.assert_array_equal(got.counts, want.counts)
+        np.testing.assert_array_equal(got.first, want.first)
+        check_calling(fixtures, name, got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step_type", ["Gibbs", "Metropolis-Hastings"])
+def test_calling_fit_posterior_batch_matches_fit_then_host_summaries(step_type):
+    from mchap_b200.calling import CallingMCMC
+    from mchap_b200.calling.classes import AllelesTraceTally
+    from mchap_b200.synth import synth_haplotype_panel
+
+    for ploidy, n_haps, depth, max_unique in [(4, 12, 30, 64), (4, 6, 3, 2), (2, 5, 8, 64)]:
+        n_items = 16
+        batch, panels, _ = synth_haplotype_panel(n_items, n_haps, 6, ploidy, depth=depth, seed=ploidy + n_haps)
+        reads = [batch.item(i)[0] for i in range(n_items)]
+        counts = [batch.item(i)[1] for i in range(n_items)]
+        model = CallingMCMC(ploidy=ploidy, haplotypes=panels[0], steps=200, chains=2, random_seed=9,
+                            step_type=step_type, prior=(0.1, None))
+        traces = model.fit_batch(reads, counts, haplotypes_list=list(panels))
+        tallies = model.fit_posterior_batch(reads, counts, burn=50, haplotypes_list=list(panels), max_unique=max_unique)
+        for i in range(n_items):
+            burnt = traces[i].burn(50)
+            want = AllelesTraceTally.from_trace(burnt)
+            np.testing.assert_array_equal(tallies[i].states, want.states, err_msg="item %d" % i)
+            np.testing.assert_array_equal(tallies[i].counts, want.counts)
+            np.testing.assert_array_equal(tallies[i].first, want.first)
+            a, b = tallies[i].posterior(), burnt.posterior()
+            np.testing.assert_array_equal(a.genotypes, b.genotypes)
+            np.testing.assert_array_equal(a.probabilities, b.probabilities)
+            assert tallies[i].replicate_incongruence(0.6) == burnt.replicate_incongruence(0.6)
+            np.testing.assert_array_equal(np.stack(tallies[i].posterior_frequencies()),
+                                          np.stack(burnt.posterior_frequencies()))
