@@ -65,6 +65,12 @@ struct AsmArgs {
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
         o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache,
         o_wmap, o_inv;
+    // tres = state slots resident in shared memory: tmax normally; 1 when the per-temperature
+    // tables of a large shape would otherwise leave only one warp per SM — then the slot of the
+    // temperature being stepped is swapped in from / out to slot_backing (global memory, L2)
+    int32_t tres;
+    int32_t slot_bytes;          // bytes of one slot in the backing store
+    unsigned char *slot_backing; // [grid warps][tmax][slot_bytes], only if tres < tmax
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
@@ -306,6 +312,36 @@ __device__ __noinline__ double eval_rows(const double *q_lane, const double *cnt
     return warp_sum(acc);
 }
 
+// Swap one state slot (keys, product rows and their float32 shadows, per-read sums, epochs, memo
+// tables) between the resident slot 0 in shared memory and slot `slot` of this warp's backing
+// store.  Out of line: only shapes whose tables do not fit use it.
+template <int CH>
+__device__ __noinline__ void slot_copy(const AsmArgs &a, unsigned char *sm, int lane, int slot, bool store) {
+    constexpr int UPAD = CH * 32;
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned char *back = a.slot_backing + ((size_t)warp_global * a.tmax + slot) * a.slot_bytes;
+    const int32_t offs[7] = {a.o_q, a.o_mcache, a.o_key, a.o_scache, a.o_q32, a.o_rpc, a.o_epoch};
+    const int32_t lens[7] = {a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, MCHB_SCACHE_N * (int)sizeof(ScEntry),
+                             a.pmax * UPAD * 4, UPAD * 4, 8};
+    __syncwarp();
+    size_t boff = 0;
+#pragma unroll 1
+    for (int r = 0; r < 7; r++) {
+        uint32_t *sp = reinterpret_cast<uint32_t *>(sm + offs[r]);
+        uint32_t *bp = reinterpret_cast<uint32_t *>(back + boff);
+        const int words = lens[r] >> 2;
+        if (store) {
+#pragma unroll 4
+            for (int i = lane; i < words; i += 32) bp[i] = sp[i];
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < words; i += 32) sp[i] = bp[i];
+        }
+        boff += (size_t)((lens[r] + 7) & ~7);
+    }
+    __syncwarp();
+}
+
 template <int CH, bool PRIOR>
 struct AsmCtx {
     static constexpr int UPAD = CH * 32;
@@ -346,6 +382,14 @@ struct AsmCtx {
 
     __device__ __forceinline__ int slot(int t) const { return (int)((slots >> (4 * t)) & 15u); }
     __device__ __forceinline__ uint64_t *keys(int s) const { return key() + s * P; }
+    // keys of state slot s wherever it lives: shared memory, or the backing store when only one
+    // slot is resident (every slot is stored right after its temperature was stepped)
+    __device__ __forceinline__ const uint64_t *slot_keys(int s) const {
+        if (CH < 2 || a.tres >= a.tmax) return keys(s);  // (the CH = 1 kernels never swap: see launch_assemble)
+        const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const size_t key_off = (size_t)a.pmax * UPAD * 8 + (size_t)2 * a.pmax * a.nmax * 8;  // after q and mcache
+        return reinterpret_cast<const uint64_t *>(a.slot_backing + ((size_t)warp_global * a.tmax + s) * a.slot_bytes + key_off);
+    }
 
     // jitutils.random_choice (77-92): p (uniform, shared memory) is overwritten by its cumsum
     __device__ __forceinline__ int random_choice_inplace(double *p, int n) {
@@ -372,13 +416,13 @@ struct AsmCtx {
     }
     __device__ __forceinline__ double *qrow_lane(int s, int h) const { return q() + (size_t)(s * P + h) * UPAD + lane; }
     // spare rows (two per warp) that hold the old rows of a proposal while it is installed
-    __device__ __forceinline__ double *spare_lane(int k) const { return q() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
+    __device__ __forceinline__ double *spare_lane(int k) const { return q() + (size_t)(a.tres * a.pmax + k) * UPAD + lane; }
 
     __device__ __forceinline__ float *q32() const { return reinterpret_cast<float *>(sm + a.o_q32); }
     __device__ __forceinline__ float *rat() const { return reinterpret_cast<float *>(sm + a.o_rat); }
     __device__ __forceinline__ float *c32() const { return reinterpret_cast<float *>(sm + a.o_c32); }
     __device__ __forceinline__ float *qrow32_lane(int s, int h) const { return q32() + (size_t)(s * P + h) * UPAD + lane; }
-    __device__ __forceinline__ float *spare32_lane(int k) const { return q32() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane; }
+    __device__ __forceinline__ float *spare32_lane(int k) const { return q32() + (size_t)(a.tres * a.pmax + k) * UPAD + lane; }
 
     // ---- memo of screened quantities.  Chains sit in one state for long stretches; the screened
     // (float32) acceptance bounds are functions of the state only, so they are kept per slot and
@@ -664,7 +708,7 @@ struct AsmCtx {
         while (done < n && !err) {
             // screened quantities of this slot's sub-steps are still valid if the state is the
             // one they were computed for
-            const bool memo_ok = epoch()[a.tmax + s] == epoch()[s];
+            const bool memo_ok = epoch()[a.tres + s] == epoch()[s];
             const int i = done + lane;
             const bool active = i < n;
             const int hj = pm[active ? i : done];
@@ -860,7 +904,7 @@ struct AsmCtx {
         }
         // every bi-allelic sub-step was screened from one and the same state: keep the memo
         __syncwarp();
-        if (!err && epoch()[s] == epoch_at_start && lane == 0) epoch()[a.tmax + s] = epoch_at_start;
+        if (!err && epoch()[s] == epoch_at_start && lane == 0) epoch()[a.tres + s] = epoch_at_start;
         __syncwarp();
     }
 
@@ -1150,8 +1194,8 @@ struct AsmCtx {
         double llk_j = lt[t - 1];
         double prior_i = 0.0, prior_j = 0.0;
         if (PRIOR) {
-            prior_i = prior_of_keys(keys(si), -1, 0, -1, 0);
-            prior_j = prior_of_keys(keys(sj), -1, 0, -1, 0);
+            prior_i = prior_of_keys(slot_keys(si), -1, 0, -1, 0);
+            prior_j = prior_of_keys(slot_keys(sj), -1, 0, -1, 0);
         }
         double post_i = llk_i + prior_i, post_j = llk_j + prior_j;
         double frac_1 = (post_j - post_i) * temp_i;
@@ -1396,10 +1440,14 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
     {
         // state epochs start at 1 and only grow; memo entries start at epoch 0 (= never valid)
         uint32_t *e = c.epoch();
-        for (int i = lane; i < 2 * a.tmax; i += 32) e[i] = i < a.tmax ? 1u : 0u;
+        for (int i = lane; i < 2 * a.tres; i += 32) e[i] = i < a.tres ? 1u : 0u;
         ScEntry *sc0 = c.scache(0);
-        for (int i = lane; i < a.tmax * MCHB_SCACHE_N; i += 32) sc0[i].epoch = 0u;
+        for (int i = lane; i < a.tres * MCHB_SCACHE_N; i += 32) sc0[i].epoch = 0u;
         __syncwarp();
+        if (CH >= 2 && a.tres < a.tmax) {
+            // every slot of the backing store starts from the same empty memo state
+            for (int t = 0; t < a.tmax; t++) slot_copy<CH>(a, c.sm, lane, t, true);
+        }
     }
 
     for (;;) {
@@ -1511,12 +1559,29 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
                 __syncwarp();
                 // ---- all temperatures start from the same state (mcmc.py:296-303)
                 c.slots = 0x76543210u;
+                // one resident slot, the others in the backing store (never in the CH = 1 kernels,
+                // whose hot loop stays free of the swap code)
+                const bool swap = CH >= 2 && a.tres < a.tmax && T > 1;
+                if (swap) {
+                    uint64_t *kk = reinterpret_cast<uint64_t *>(c.oll());  // the initial keys survive the slot loads
+                    for (int h = lane; h < P; h += 32) kk[h] = k0[h];
+                    __syncwarp();
+#pragma unroll 1
+                    for (int t = 0; t < T; t++) {
+                        slot_copy<CH>(a, c.sm, lane, t, false);
+#pragma unroll 1
+                        for (int h = 0; h < P; h++) c.commit(0, h, kk[h]);
+                        slot_copy<CH>(a, c.sm, lane, t, true);
+                    }
+                }
                 {
+                    if (!swap) {
 #pragma unroll 1
-                    for (int h = 0; h < P; h++) {
-                        const uint64_t k = k0[h];
+                        for (int h = 0; h < P; h++) {
+                            const uint64_t k = k0[h];
 #pragma unroll 1
-                        for (int t = 0; t < T; t++) c.commit(t, h, k);
+                            for (int t = 0; t < T; t++) c.commit(t, h, k);
+                        }
                     }
                     __syncwarp();
                     double llk0 = c.eval_llk(0);
@@ -1533,15 +1598,20 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
 #pragma unroll 1
                     for (int t = 0; t < T && !c.err; t++) {
                         llk = lt[t];
-                        const int s = c.slot(t);
+                        int s = c.slot(t);
                         const double temp = temps[t];
                         if (isnan(llk)) {
                             c.err = MCHB_ITEM_NAN_LLK;
                             break;
                         }
+                        if (swap) {
+                            slot_copy<CH>(a, c.sm, lane, s, false);
+                            s = 0;
+                        }
                         c.mutation_compound_step(s, temp, llk);
                         if (c.err) break;
                         c.structural_substeps(s, temp, llk, brow, blen);
+                        if (swap) slot_copy<CH>(a, c.sm, lane, c.slot(t), true);
                         if (c.err) break;
                         if (t > 0) c.chain_swap_step(t, temp, temps[t - 1], llk);
                         __syncwarp();
@@ -1550,7 +1620,7 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
                     if (c.err) break;
                     // ---- record the cold chain (state of the last temperature, mcmc.py:418-425)
                     {
-                        const uint64_t *ks = c.keys(c.slot(T - 1));
+                        const uint64_t *ks = c.slot_keys(c.slot(T - 1));
                         int8_t *dst = ogc + (size_t)step * step_sz;
                         __syncwarp();
 #pragma unroll 1

@@ -54,6 +54,7 @@ enum Slot {
     S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
     S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS, S_CHUNKS,
     S_TITEMS, S_TGENO, S_TSTATES, S_TCOUNTS, S_TFIRST, S_TRESULTS,
+    S_BACKING0, S_BACKING1, S_BACKING2, S_BACKING3, S_BACKING4, S_BACKING5, S_BACKING6, S_BACKING7, S_BACKING8, S_BACKING9,
     S_NSLOTS
 };
 
@@ -358,7 +359,7 @@ struct AsmGeom {
 };
 
 // per-warp shared memory layout: fills the byte offsets in args, returns the region size
-size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
+size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     const size_t upad = (size_t)ch * 32;
     size_t off = 0;
     auto take = [&](size_t bytes, size_t align) {
@@ -369,14 +370,14 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     };
     take((size_t)g.nmax * g.amax * upad * 8, 16);                      // Rt at 0
     args.o_cnt = take(upad * 8, 8);
-    args.o_q = take(((size_t)g.tmax * g.pmax + 2) * upad * 8, 8);  // + 2 spare rows
+    args.o_q = take(((size_t)tres * g.pmax + 2) * upad * 8, 8);  // + 2 spare rows
     args.o_dist = take((size_t)g.nmax * g.amax * 8, 8);
     args.o_oll = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_opr = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_lgdisp = take((size_t)(g.pmax + 2) * 8, 8);
     args.o_homlp = take((size_t)std::max(g.amax, g.pmax) * 8, 8);  // also the prior's row scratch
     args.o_llk_t = take((size_t)g.tmax * 8, 8);
-    args.o_key = take((size_t)g.tmax * g.pmax * 8, 8);
+    args.o_key = take((size_t)tres * g.pmax * 8, 8);
     args.o_sc = take((size_t)SC_COUNT * 8, 8);
     args.o_perm = take((size_t)g.pmax * g.nmax * 2, 2);
     args.o_het = take((size_t)g.nmax, 1);
@@ -387,14 +388,14 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
     args.o_ivb = take((size_t)g.nmax + 2, 1);
     args.o_ivp = take((size_t)g.nmax + 2, 1);
     args.o_ring = take(128 * 4, 4);
-    args.o_q32 = take(((size_t)g.tmax * g.pmax + 2) * upad * 4, 4);
+    args.o_q32 = take(((size_t)tres * g.pmax + 2) * upad * 4, 4);
     args.o_rat = take((size_t)g.nmax * 2 * upad * 4, 4);
     args.o_c32 = take(upad * 4, 4);
-    args.o_rpc = take((size_t)g.tmax * upad * 4, 4);
+    args.o_rpc = take((size_t)tres * upad * 4, 4);
     args.o_bcs = take((size_t)(g.maxopt + 1) * 8, 8);
-    args.o_epoch = take((size_t)g.tmax * 2 * 4, 4);
-    args.o_mcache = take((size_t)g.tmax * 2 * g.pmax * g.nmax * 8, 8);
-    args.o_scache = take((size_t)g.tmax * MCHB_SCACHE_N * sizeof(ScEntry), 8);
+    args.o_epoch = take((size_t)tres * 2 * 4, 8);
+    args.o_mcache = take((size_t)tres * 2 * g.pmax * g.nmax * 8, 8);
+    args.o_scache = take((size_t)tres * MCHB_SCACHE_N * sizeof(ScEntry), 8);
     args.o_wmap = take((size_t)g.pmax * g.nmax * 2, 2);
     args.o_inv = take(32 * 4, 4);
     return (off + 15) & ~(size_t)15;
@@ -402,11 +403,29 @@ size_t asm_layout(const AsmGeom &g, int ch, AsmArgs &args) {
 
 template <int CH, bool PRIOR>
 int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const AsmGeom &g, int n_items_class,
-                    bool overlap_previous) {
-    const size_t per_warp = asm_layout(g, CH, args);
-    int warps_per_cta = 4;
-    while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
-    if (per_warp * warps_per_cta > (size_t)h->smem_optin) {
+                    bool overlap_previous, int backing_slot) {
+    // all temperatures' state slots resident — unless that leaves fewer than four warps per CTA:
+    // then one resident slot, the others swapped through a backing store in global memory
+    int tres = g.tmax;
+    size_t per_warp = asm_layout(g, CH, tres, args);
+    if (CH >= 2 && g.tmax > 1 && per_warp * 4 > (size_t)h->smem_optin) {
+        tres = 1;
+        per_warp = asm_layout(g, CH, tres, args);
+    }
+    // warps per CTA: the value (4, 3, 2, 1) that keeps most warps resident per SM
+    // (228 KB of shared memory per SM, 1 KB reserved per resident CTA)
+    int warps_per_cta = 0, best = 0;
+    if (per_warp * 4 <= (size_t)h->smem_optin) warps_per_cta = 4;  // the usual case
+    for (int w = 4; w >= 1 && warps_per_cta == 0; w--) {
+        if (per_warp * w > (size_t)h->smem_optin) continue;
+        const int resident = (int)((size_t)(228 * 1024) / (per_warp * w + 1024)) * w;
+        if (resident > best) best = resident;
+    }
+    for (int w = 4; w >= 1 && warps_per_cta == 0; w--)
+        if (per_warp * w <= (size_t)h->smem_optin &&
+            (int)((size_t)(228 * 1024) / (per_warp * w + 1024)) * w == best)
+            warps_per_cta = w;
+    if (warps_per_cta == 0) {
         h->err = "assemble item needs more shared memory than one CTA can have";
         return MCHB_ERR_ARGUMENT;
     }
@@ -424,6 +443,21 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
     args.tmax = g.tmax;
     args.maxopt = g.maxopt;
     args.smem_per_warp = (int)per_warp;
+    args.tres = tres;
+    args.slot_bytes = 0;
+    args.slot_backing = nullptr;
+    if (tres < g.tmax) {
+        const size_t upad = (size_t)CH * 32;
+        auto r8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+        const size_t slot_bytes = (r8(g.pmax * upad * 8) + r8((size_t)2 * g.pmax * g.nmax * 8) + r8((size_t)g.pmax * 8) +
+                                   r8(MCHB_SCACHE_N * sizeof(ScEntry)) + r8(g.pmax * upad * 4) + r8(upad * 4) + r8(8) + 15) &
+                                  ~(size_t)15;
+        void *back;
+        int rc = ensure(h, backing_slot, slot_bytes * (size_t)g.tmax * (size_t)grid * warps_per_cta, &back);
+        if (rc) return rc;
+        args.slot_bytes = (int32_t)slot_bytes;
+        args.slot_backing = (unsigned char *)back;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
@@ -704,14 +738,14 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                 }
                 const int n_c = (int)todo[c].size();
                 switch (c) {
-                    case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c, chained); break;
-                    case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c, chained); break;
-                    case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c, chained); break;
-                    case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c, chained); break;
-                    case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c, chained); break;
-                    case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c, chained); break;
-                    case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c, chained); break;
-                    default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c, chained); break;
+                    case 0: rc = launch_assemble<1, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                 }
                 if (rc) return rc;
                 chained = true;
