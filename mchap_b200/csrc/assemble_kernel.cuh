@@ -970,7 +970,6 @@ struct AsmCtx {
         {
             double smax = INFINITY;
             if (B == 1 && n_options <= 32) {
-                const int n_ret = structural_options(my_lin, lout, P, step_type, nullptr, nullptr);
                 const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
                 const float *rt = rat() + lane;
                 const float *cw = c32() + lane;
@@ -1016,7 +1015,9 @@ struct AsmCtx {
                     const bool sane = __all_sync(MCHB_FULL, ok);
                     double lprior_ratio = 0.0;
                     if (PRIOR) lprior_ratio = prior_of_labels(__shfl_sync(MCHB_FULL, my_lin, k), lout) - lprior;
-                    const double lprop = LOG_INV_INT[__shfl_sync(MCHB_FULL, n_ret, k)] - log_proposal;
+                    // the proposal ratio is log(1 / n_reverse) - log(1 / n_options) <= log(n_options): the
+                    // bound spares the screening pass the reverse-move count of every option
+                    const double lprop = -log_proposal;
                     const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
                     smax = sane ? fmax(smax, mh32) : INFINITY;  // fmax ignores NaN: treat NaN as inconclusive
                     if (isnan(mh32)) smax = INFINITY;
