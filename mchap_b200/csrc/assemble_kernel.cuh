@@ -757,7 +757,7 @@ struct AsmCtx {
                 // (current allele 0) — see the cumulative sums in base_step — so a sub-step whose
                 // screened mh is below log(t) - margin is certainly rejected and needs no exact
                 // evaluation; everything else ("needy") is decided exactly below.
-                double a32 = 0.0;
+                float a32f = 0.f;  // float32 accumulation: rounding <= U * 2^-24 * |llk|, far inside the margin
                 bool sane = true;
                 {
                     // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.
@@ -773,9 +773,10 @@ struct AsmCtx {
                         const float rc_r = rc[r];
                         const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
                         sane = sane && (rp > 1e-4f * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
-                        a32 += (double)(__logf(rp) * cw[r]);
+                        a32f = fmaf(__logf(rp), cw[r], a32f);
                     }
                 }
+                const double a32 = (double)a32f;
                 d32 = sane ? (a32 - llk) + lprior_ratio : INFINITY;  // +inf: never screened out
                 if (mine) {
                     mc[0] = d32;
