@@ -397,6 +397,7 @@ struct AsmCtx {
 #pragma unroll 1
         for (int i = 0; i < n; i++) {
             acc += p[i];
+            __syncwarp();  // every lane has read p[i] before any lane overwrites it
             p[i] = acc;
         }
         double u = ws.next_double();
@@ -588,16 +589,21 @@ struct AsmCtx {
 #pragma unroll 1
         for (int i = 0; i < n_all; i++) {
             const double p = dexp(op[i] - ln_opts);
+            __syncwarp();  // uniform code updating shared memory in place: read by all lanes, then written
             op[i] = p;
             sum += p;
         }
+        __syncwarp();
         op[cur] = 1 - sum;
+        __syncwarp();
         double cacc = 0.0;
 #pragma unroll 1
         for (int i = 0; i < n_all; i++) {
             cacc += op[i];
+            __syncwarp();
             op[i] = cacc;
         }
+        __syncwarp();
         const int choice = searchsorted_right(op, n_all, u);
         if (choice >= n_all) {
             err = MCHB_ITEM_CHOICE_RANGE;
@@ -1101,16 +1107,21 @@ struct AsmCtx {
 #pragma unroll 1
         for (int i = 0; i <= n_options; i++) {
             const double p = dexp(op[i] - ln_opts);
+            __syncwarp();  // uniform code updating shared memory in place: read by all lanes, then written
             op[i] = p;
             sum += p;
         }
+        __syncwarp();
         op[n_options] = 1 - sum;
+        __syncwarp();
         double acc = 0.0;
 #pragma unroll 1
         for (int i = 0; i <= n_options; i++) {
             acc += op[i];
+            __syncwarp();
             op[i] = acc;
         }
+        __syncwarp();
         const int choice = searchsorted_right(op, n_options + 1, u);
         if (choice < n_options) {
             const int h0 = o0[choice], h1 = o1[choice];
@@ -1367,6 +1378,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
                 opr[al] = v;
                 s1 += v;
             }
+            __syncwarp();  // dist is rewritten below: every lane is done reading it
             double s2 = 0.0;
 #pragma unroll 1
             for (int al = 0; al < A; al++) {
@@ -1375,7 +1387,11 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
                 s2 += v;
             }
 #pragma unroll 1
-            for (int al = 0; al < A; al++) dist[k * A + al] = dist[k * A + al] / s2;
+            for (int al = 0; al < A; al++) {
+                const double v = dist[k * A + al] / s2;
+                __syncwarp();
+                dist[k * A + al] = v;
+            }
             __syncwarp();
         }
     }

@@ -172,10 +172,14 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                 int v = ini[i];
                 int j = i - 1;
                 __syncwarp();
-                while (j >= 0 && ini[j] > v) {
-                    ini[j + 1] = ini[j];
+                while (j >= 0) {  // uniform code on shared memory: read, barrier, then write
+                    const int x = ini[j];
+                    if (!(x > v)) break;
+                    __syncwarp();
+                    ini[j + 1] = x;
                     j--;
                 }
+                __syncwarp();
                 ini[j + 1] = v;
                 __syncwarp();
             }
@@ -394,10 +398,14 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                     int v = gs[i];
                     int j = i - 1;
                     __syncwarp();
-                    while (j >= 0 && gs[j] > v) {
-                        gs[j + 1] = gs[j];
+                    while (j >= 0) {  // uniform code on shared memory: read, barrier, then write
+                        const int x = gs[j];
+                        if (!(x > v)) break;
+                        __syncwarp();
+                        gs[j + 1] = x;
                         j--;
                     }
+                    __syncwarp();
                     gs[j + 1] = v;
                     __syncwarp();
                 }
