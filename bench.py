@@ -39,8 +39,8 @@ WORKLOAD = ("synthetic tetraploid assemble: 10k loci x 8 SNVs x 100 samples, dep
 
 
 # DRAM bytes per (locus, sample) item of assemble_kernel<1,false>, from the committed ncu capture
-# (profiles/README.md): 253.8 MB read + written by a launch of 1964 items (traces dominate)
-NCU_DRAM_BYTES_PER_ITEM = 129226.0
+# (profiles/README.md): 250.2 MB read + written by a launch of 1964 items (traces dominate)
+NCU_DRAM_BYTES_PER_ITEM = 127416.0
 
 def parse_args():
     ap = argparse.ArgumentParser()
