@@ -15,6 +15,9 @@ JSON keys follow the round contract: value (device-resident throughput, CUDA eve
 ranks), e2e (host buffers through the C ABI, H2D + D2H inside the timed region), roofline
 (FP64 SIMT pipe: algorithmic flops of SURVEY.md section 8(d) / kernel time, against a DFMA
 probe measured live), cpu_baseline (C oracle on the host cores, bounded sample), clocks.
+Secondary objects on the same line: e2e_posterior (the same workload as the application consumes
+it: traces kept in HBM, tallies of the burnt trace returned) and call_exact (genotype
+likelihoods/s of configs[2]).
 """
 import argparse
 import json

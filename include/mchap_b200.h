@@ -128,7 +128,12 @@ int mchb_log_likelihood_batch(mchb_handle *h, int mem, const mchb_llk_item *item
  * f64[chains, steps] at out_llks + llks_off.  The RNG stream of an item is the MT19937
  * stream of `seed` from its start (the reference re-seeds at the top of every fit), consumed
  * with numba's word->value rules in the reference's call order: chains one after another,
- * temperatures ascending inside a step. */
+ * temperatures ascending inside a step.
+ *
+ * With MCHB_MEM_HOST outputs of 256 MB or more the batch is cut into chunks of consecutive
+ * items and the traces of a finished chunk are copied to the host while later chunks are still
+ * being sampled (see mchb_last_host_chunks); page-locked output buffers make those copies
+ * asynchronous, pageable ones work too. */
 typedef struct {
     int64_t reads_off;       /* doubles */
     int64_t counts_off;      /* int64 elements; ignored if counts == NULL */
