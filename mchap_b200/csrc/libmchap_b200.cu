@@ -498,9 +498,9 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         h->err = "bad assemble parameters";
         return MCHB_ERR_ARGUMENT;
     }
-    constexpr int NCLS = 8;
+    constexpr int NCLS = 10;
     // ---- validate, classify by unique-read chunk count and prior use, collect seeds
-    std::vector<int32_t> order[NCLS];  // class = 2 * log2(CH) + has_prior, CH = 1, 2, 4, 8
+    std::vector<int32_t> order[NCLS];  // class = 2 * (index of CH in {1, 2, 3, 4, 8}) + has_prior
     AsmGeom geom[NCLS];
     std::map<uint32_t, int32_t> seed_index;
     std::vector<uint32_t> seeds;
@@ -535,7 +535,8 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         if (it.n_pos == 0) {  // nothing to sample: empty traces, NaN llks are written by the host shim
             continue;
         }
-        int cls = 2 * (it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 128 ? 2 : 3) + (std::isnan(it.inbreeding) ? 0 : 1);
+        int cls = 2 * (it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 96 ? 2 : it.n_reads <= 128 ? 3 : 4) +
+                  (std::isnan(it.inbreeding) ? 0 : 1);
         order[cls].push_back((int32_t)i);
         AsmGeom &g = geom[cls];
         g.nmax = std::max(g.nmax, it.n_pos);
@@ -566,7 +567,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     if ((rc = ensure(h, S_BREAKS, sizeof(double) * (size_t)pp.break_rows * pp.break_stride, &dbreaks))) return rc;
     if ((rc = ensure(h, S_BREAKLEN, sizeof(int32_t) * (size_t)pp.break_rows, &dbreaklen))) return rc;
     if ((rc = ensure(h, S_TEMPS, sizeof(double) * (size_t)pp.temperatures_len, &dtemps))) return rc;
-    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 8, &dcounter))) return rc;
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 16, &dcounter))) return rc;
     if ((rc = ensure(h, S_RESULTS, sizeof(mchb_item_result) * (size_t)n_items, &dresults))) return rc;
     CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_assemble_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(dstream, item_stream.data(), sizeof(int32_t) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
@@ -671,7 +672,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         }
         void *dorder;
         if ((rc = ensure(h, S_ORDER, sizeof(int32_t) * (size_t)total, &dorder))) return rc;
-        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 8, h->stream));
+        CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 16, h->stream));
         if (piped)
             CK(cudaMemcpyAsync(dchunk, chunk_skip.data(), sizeof(uint32_t) * (size_t)n_chunks, cudaMemcpyHostToDevice,
                                h->stream));
@@ -742,9 +743,11 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                     case 1: rc = launch_assemble<1, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                     case 2: rc = launch_assemble<2, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                     case 3: rc = launch_assemble<2, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
-                    case 4: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
-                    case 5: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
-                    case 6: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 4: rc = launch_assemble<3, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 5: rc = launch_assemble<3, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 6: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 7: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 8: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                     default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                 }
                 if (rc) return rc;

@@ -147,6 +147,7 @@ def _oracle_fit(oracle, model, reads, counts, na, seed=None, replay=None):
     (8, 16, 100, (0.01, 0.1, 0.5, 1.0), None),   # BASELINE configs[3] shape (one resident state slot, swapped)
     (8, 14, 90, (0.05, 0.4, 1.0), 0.15),         # the same path with the Dirichlet-multinomial prior
     (4, 12, 60, (0.5, 1.0), 0.3),
+    (4, 16, 135, (1.0,), None),                  # 97..128 unique reads: the four-chunk kernel
 ])
 def test_assemble_batch_vs_oracle(dev, oracle, ploidy, n_pos, depth, temps, inbreeding):
     from mchap_b200 import DenovoMCMC
