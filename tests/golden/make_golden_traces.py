@@ -27,7 +27,7 @@ sys.path[:0] = [_stub, REF, ROOT]
 import numpy as np  # noqa: E402
 
 import mchap  # noqa: E402
-from mchap.assemble.mcmc import DenovoMCMC  # noqa: E402
+from mchap.assemble.mcmc import DenovoMCMC, _point_beta_probabilities  # noqa: E402
 from mchap.assemble.classes import GenotypeMultiTrace  # noqa: E402
 from mchap.calling.classes import GenotypeAllelesMultiTrace  # noqa: E402
 
@@ -162,10 +162,23 @@ def calling_cases():
     OUT["n_calling"] = np.int64(k)
 
 
+def host_tables():
+    """Host-side tables the device call takes as inputs: the break-point distributions of
+    _point_beta_probabilities (assemble/mcmc.py:429-452) for every number of variable positions."""
+    k = 0
+    for a, b in [(1.0, 3.0), (1.0, 1.0), (2.5, 0.7)]:
+        for n in list(range(1, 18)) + [32, 64, 255]:
+            OUT["beta%d_par" % k] = np.array([n, a, b], dtype=np.float64)
+            OUT["beta%d_out" % k] = _point_beta_probabilities(n, a, b)
+            k += 1
+    OUT["n_beta"] = np.int64(k)
+
+
 if __name__ == "__main__":
     sampled_cases()
     synthetic_cases()
     calling_cases()
+    host_tables()
     path = os.path.join(HERE, "reference_trace_classes.npz")
     np.savez_compressed(path, **OUT)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(OUT), os.path.getsize(path) / 1024))

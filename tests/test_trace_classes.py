@@ -253,3 +253,23 @@ def test_calling_fit_posterior_batch_matches_fit_then_host_summaries(step_type):
             assert tallies[i].replicate_incongruence(0.6) == burnt.replicate_incongruence(0.6)
             np.testing.assert_array_equal(np.stack(tallies[i].posterior_frequencies()),
                                           np.stack(burnt.posterior_frequencies()))
+
+
+def test_break_point_tables_match_reference(fixtures):
+    """The break-point distributions handed to the device (host-side scipy, like the reference's
+    _point_beta_probabilities, assemble/mcmc.py:429-452) and the rows of break_table built from them."""
+    from mchap_b200.assemble.mcmc import break_table, point_beta_probabilities
+
+    n_cases = int(fixtures["n_beta"])
+    assert n_cases >= 60
+    for k in range(n_cases):
+        n, a, b = fixtures["beta%d_par" % k]
+        want = fixtures["beta%d_out" % k]
+        np.testing.assert_array_equal(point_beta_probabilities(int(n), a, b), want)
+        if int(n) <= 32:
+            table, lens = break_table(int(n), a, b)
+            assert lens[int(n)] == len(want)
+            np.testing.assert_array_equal(table[int(n), : len(want)], want)
+    table, lens = break_table(6, n_intervals=3)   # fixed number of intervals (mcmc.py:214-217)
+    assert list(lens[1:]) == [3] * 6
+    np.testing.assert_array_equal(table[4, :3], [0.0, 0.0, 1.0])
