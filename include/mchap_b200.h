@@ -321,6 +321,38 @@ int mchb_call_mcmc_tally_batch(mchb_handle *h, const mchb_call_mcmc_params *para
                                int32_t *out_counts, int32_t *out_first, int64_t tallies_len,
                                mchb_item_result *results, mchb_item_result *tally_results);
 
+/* ---- read encoding + de-duplication ------------------------------------------------------
+ * Replaces, for a batch of (locus, sample) items, what mchap/application/baseclass.py:194-209
+ * does between the BAM reader and the samplers: encoding/integer/transcode.py:16-77
+ * as_probabilistic (through io/bam.py:251-289 encode_read_distributions) followed by
+ * mset.unique_counts (mset.py:242-284, 361-392).
+ *
+ * Item i: calls int8[n_reads, n_pos] (allele index per read and position, < 0 = gap) at
+ * calls + calls_off; probs f64[n_reads, n_pos] = probability that the call is correct (the host
+ * computes (1 - error_rate) * prob_of_qual(quals) like io/bam.py:281-286) at probs + probs_off;
+ * n_alleles int8[n_pos] at n_alleles + nalleles_off.  Outputs: the distinct encoded reads
+ * f64[n_unique, n_pos, max_allele] in order of first occurrence at out_reads + reads_off
+ * (capacity n_reads rows) and their counts int64[n_unique] at out_counts + counts_off (capacity
+ * n_reads); results[i].n_het = n_unique.  Element (r, j, a): probs[r, j] if a is the call,
+ * (1 - probs[r, j]) / error_factor otherwise, NaN (numpy's np.nan bit pattern) at gaps, 0 where
+ * a >= n_alleles[j] — bit-identical to the reference, so that the byte-wise de-duplication and
+ * the order of the unique reads (which fixes the summation order of every log-likelihood) are
+ * the reference's. */
+typedef struct {
+    int64_t calls_off;       /* int8 elements */
+    int64_t probs_off;       /* doubles */
+    int64_t nalleles_off;    /* int8 elements */
+    int64_t reads_off;       /* doubles into out_reads */
+    int64_t counts_off;      /* int64 elements into out_counts */
+    int32_t n_reads, n_pos, max_allele, reserved;
+} mchb_encode_item;
+
+int mchb_encode_reads_batch(mchb_handle *h, int mem, const mchb_encode_item *items, int64_t n_items,
+                            const int8_t *calls, int64_t calls_len, const double *probs,
+                            int64_t probs_len, const int8_t *n_alleles, int64_t n_alleles_len,
+                            double error_factor, double *out_reads, int64_t out_reads_len,
+                            int64_t *out_counts, int64_t out_counts_len, mchb_item_result *results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,20 @@ class TallyItem(C.Structure):
     ]
 
 
+class EncodeItem(C.Structure):
+    _fields_ = [
+        ("calls_off", C.c_int64),
+        ("probs_off", C.c_int64),
+        ("nalleles_off", C.c_int64),
+        ("reads_off", C.c_int64),
+        ("counts_off", C.c_int64),
+        ("n_reads", C.c_int32),
+        ("n_pos", C.c_int32),
+        ("max_allele", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class CallMcmcParams(C.Structure):
     _fields_ = [
         ("steps", C.c_int32),
@@ -168,7 +182,7 @@ SYMBOLS = [
     "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
     "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
-    "mchb_call_mcmc_tally_batch",
+    "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch",
 ]
 
 
@@ -255,6 +269,11 @@ def load():
         L.mchb_call_mcmc_tally_batch.argtypes = [
             vp, C.POINTER(CallMcmcParams), vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
             vp, C.c_int64, vp, C.c_int32, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp,
+        ]
+        L.mchb_encode_reads_batch.restype = C.c_int
+        L.mchb_encode_reads_batch.argtypes = [
+            vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_double, vp, C.c_int64,
+            vp, C.c_int64, vp,
         ]
         _lib = L
         return _lib

@@ -17,6 +17,7 @@
 #include "exact_kernel.cuh"
 #include "call_mcmc_kernel.cuh"
 #include "tally_kernel.cuh"
+#include "encode_kernel.cuh"
 
 using namespace mchb;
 
@@ -54,6 +55,7 @@ enum Slot {
     S_WORDS, S_SEEDS, S_STREAM, S_BREAKS, S_BREAKLEN, S_TEMPS, S_COUNTER, S_GENO, S_AUX0, S_AUX1,
     S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS, S_CHUNKS,
     S_TITEMS, S_TGENO, S_TSTATES, S_TCOUNTS, S_TFIRST, S_TRESULTS,
+    S_EITEMS, S_ECALLS, S_EPROBS, S_ENALL, S_EREADS, S_ECOUNTS, S_ERESULTS,
     S_BACKING0, S_BACKING1, S_BACKING2, S_BACKING3, S_BACKING4, S_BACKING5, S_BACKING6, S_BACKING7, S_BACKING8, S_BACKING9,
     S_NSLOTS
 };
@@ -1500,4 +1502,101 @@ extern "C" int mchb_call_mcmc_tally_batch(mchb_handle *h, const mchb_call_mcmc_p
         if (results[i].status != MCHB_ITEM_OK) titems[(size_t)i].steps = 0;
     return tally_run(h, 4, MCHB_MEM_DEVICE, MCHB_MEM_HOST, titems.data(), n_items, (const int8_t *)doa, alleles_len,
                      (int8_t *)out_states, out_states_len, out_counts, out_first, tallies_len, tally_results);
+}
+
+// ------------------------------------------------------------ N2 read encoding + de-duplication
+extern "C" int mchb_encode_reads_batch(mchb_handle *h, int mem, const mchb_encode_item *items, int64_t n_items,
+                                       const int8_t *calls, int64_t calls_len, const double *probs, int64_t probs_len,
+                                       const int8_t *n_alleles, int64_t n_alleles_len, double error_factor,
+                                       double *out_reads, int64_t out_reads_len, int64_t *out_counts,
+                                       int64_t out_counts_len, mchb_item_result *results) {
+    if (!h || !items || !results || n_items < 0 || !out_reads || !out_counts) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    if (n_items > 0x7fffffff) {
+        h->err = "too many items in one call";
+        return MCHB_ERR_ARGUMENT;
+    }
+    int rmax = 1, emax = 1;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_encode_item &it = items[i];
+        const int64_t rn = (int64_t)it.n_reads * it.n_pos, e = (int64_t)it.n_pos * it.max_allele;
+        bool bad = it.n_reads < 0 || it.n_pos < 0 || it.max_allele < 0 || it.n_reads > 65536 || e > 4096 ||
+                   it.calls_off < 0 || it.calls_off + rn > calls_len || it.probs_off < 0 ||
+                   it.probs_off + rn > probs_len || it.nalleles_off < 0 || it.nalleles_off + it.n_pos > n_alleles_len ||
+                   it.reads_off < 0 || it.reads_off + (int64_t)it.n_reads * e > out_reads_len || it.counts_off < 0 ||
+                   it.counts_off + it.n_reads > out_counts_len;
+        if (bad) {
+            h->err = "encode item " + std::to_string(i) + " exceeds the given array lengths or the limits "
+                     "(n_reads <= 65536, n_pos * max_allele <= 4096)";
+            return MCHB_ERR_ARGUMENT;
+        }
+        rmax = std::max(rmax, it.n_reads);
+        emax = std::max<int>(emax, (int)e);
+    }
+    int rc;
+    void *ditems, *dresults, *dcounter;
+    if ((rc = ensure(h, S_EITEMS, sizeof(mchb_encode_item) * (size_t)n_items, &ditems))) return rc;
+    if ((rc = ensure(h, S_ERESULTS, sizeof(mchb_item_result) * (size_t)n_items, &dresults))) return rc;
+    if ((rc = ensure(h, S_COUNTER, sizeof(int32_t) * 16, &dcounter))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_encode_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(dcounter, 0, sizeof(int32_t) * 16, h->stream));
+    const int8_t *dcalls, *dnall;
+    const double *dprobs;
+    double *dreads;
+    int64_t *dcounts;
+    if ((rc = stage_in(h, mem, S_ECALLS, calls, calls_len, &dcalls))) return rc;
+    if ((rc = stage_in(h, mem, S_EPROBS, probs, probs_len, &dprobs))) return rc;
+    if ((rc = stage_in(h, mem, S_ENALL, n_alleles, n_alleles_len, &dnall))) return rc;
+    if ((rc = stage_out(h, mem, S_EREADS, out_reads, out_reads_len, &dreads))) return rc;
+    if ((rc = stage_out(h, mem, S_ECOUNTS, out_counts, out_counts_len, &dcounts))) return rc;
+    if (mem == MCHB_MEM_HOST) {  // rows and counts beyond n_unique are not written by the kernel
+        CK(cudaMemsetAsync(dreads, 0, sizeof(double) * (size_t)std::max<int64_t>(out_reads_len, 1), h->stream));
+        CK(cudaMemsetAsync(dcounts, 0, sizeof(int64_t) * (size_t)std::max<int64_t>(out_counts_len, 1), h->stream));
+    }
+    size_t per_warp = ((size_t)emax * 8 + (size_t)rmax * 4 + 15) & ~(size_t)15;
+    int warps_per_cta = 4;
+    while (warps_per_cta > 1 && per_warp * warps_per_cta > (size_t)h->smem_optin) warps_per_cta >>= 1;
+    if (per_warp * warps_per_cta > (size_t)h->smem_optin) {
+        h->err = "encode item needs more shared memory than one CTA can have";
+        return MCHB_ERR_ARGUMENT;
+    }
+    const size_t smem = per_warp * warps_per_cta;
+    CK(cudaFuncSetAttribute(encode_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, encode_reads_kernel, warps_per_cta * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    EncodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.items = (const mchb_encode_item *)ditems;
+    a.n_items = (int32_t)n_items;
+    a.calls = dcalls;
+    a.probs = dprobs;
+    a.n_alleles = dnall;
+    a.error_factor = error_factor;
+    a.out_reads = dreads;
+    a.out_counts = dcounts;
+    a.results = (mchb_item_result *)dresults;
+    a.work_counter = (int32_t *)dcounter;
+    a.smem_per_warp = (int32_t)per_warp;
+    a.rmax = rmax;
+    a.emax = emax;
+    long long want = (n_items + warps_per_cta - 1) / warps_per_cta;
+    long long grid = std::max<long long>(1, std::min<long long>(want, (long long)h->sm_count * ctas_per_sm));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    encode_reads_kernel<<<(unsigned)grid, warps_per_cta * 32, smem, h->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(results, dresults, sizeof(mchb_item_result) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+    if (mem == MCHB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_reads, dreads, sizeof(double) * (size_t)out_reads_len, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_counts, dcounts, sizeof(int64_t) * (size_t)out_counts_len, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->kernel_ms += ms;
+    return MCHB_OK;
 }

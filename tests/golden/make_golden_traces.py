@@ -30,6 +30,8 @@ import mchap  # noqa: E402
 from mchap.assemble.mcmc import DenovoMCMC, _point_beta_probabilities  # noqa: E402
 from mchap.assemble.classes import GenotypeMultiTrace  # noqa: E402
 from mchap.calling.classes import GenotypeAllelesMultiTrace  # noqa: E402
+from mchap.encoding.integer import as_probabilistic  # noqa: E402
+from mchap import mset  # noqa: E402
 
 from mchap_b200.synth import synth_items  # noqa: E402
 
@@ -174,11 +176,49 @@ def host_tables():
     OUT["n_beta"] = np.int64(k)
 
 
+def encoding_cases():
+    """as_probabilistic (encoding/integer/transcode.py:16-77) + mset.unique_counts (mset.py:361-392)
+    the way application/baseclass.py:194-209 chains them (probabilities from phred qualities and an
+    extra error rate like io/bam.py:281-286)."""
+    k = 0
+    for n_reads, n_pos, amax, gap_rate, error_rate, n_quals, seed in [
+        (40, 8, 2, 0.3, 0.0024, 1, 21), (60, 8, 2, 0.5, 0.0, 3, 22), (25, 5, 4, 0.2, 0.01, 4, 23),
+        (0, 6, 2, 0.0, 0.0, 1, 24), (30, 1, 3, 0.1, 0.0024, 2, 25), (200, 12, 2, 0.6, 0.0024, 2, 26),
+        (12, 3, 2, 1.0, 0.0, 1, 27), (50, 16, 3, 0.4, 0.001, 40, 28),
+    ]:
+        rng = np.random.default_rng(seed)
+        n_alleles = rng.integers(2, amax + 1, size=n_pos) if amax > 2 else np.full(n_pos, 2)
+        haps = np.stack([rng.integers(0, n_alleles) for _ in range(4)])
+        calls = haps[rng.integers(0, 4, size=n_reads)] if n_reads else np.zeros((0, n_pos), dtype=int)
+        calls = np.array(calls, dtype=np.int8)
+        # some calls beyond the position's allele constraint, some gaps
+        flip = rng.random(calls.shape) < 0.03
+        calls[flip] = rng.integers(0, amax + 1, size=int(flip.sum()))
+        calls[rng.random(calls.shape) < gap_rate] = -1
+        quals = rng.choice(rng.integers(2, 42, size=n_quals), size=calls.shape)
+        probs = np.ones(calls.shape, dtype=float) * (1 - error_rate)
+        probs *= 1 - (10 ** (quals / -10))            # io/util.py prob_of_qual
+        dists = as_probabilistic(calls, n_alleles, probs)
+        uniq, counts = mset.unique_counts(dists)
+        name = "encode%d" % k
+        OUT[name + "_calls"] = calls
+        OUT[name + "_quals"] = quals.astype(np.int64)
+        OUT[name + "_error_rate"] = np.float64(error_rate)
+        OUT[name + "_probs"] = probs
+        OUT[name + "_n_alleles"] = n_alleles.astype(np.int8)
+        OUT[name + "_dists"] = dists
+        OUT[name + "_unique"] = uniq
+        OUT[name + "_counts"] = np.asarray(counts, dtype=np.int64)
+        k += 1
+    OUT["n_encode"] = np.int64(k)
+
+
 if __name__ == "__main__":
     sampled_cases()
     synthetic_cases()
     calling_cases()
     host_tables()
+    encoding_cases()
     path = os.path.join(HERE, "reference_trace_classes.npz")
     np.savez_compressed(path, **OUT)
     print("wrote %s: %d arrays, %.1f KB" % (path, len(OUT), os.path.getsize(path) / 1024))

@@ -62,3 +62,4 @@ def test_struct_layouts_match_the_header():
     assert _lib.AssembleItem.inbreeding.offset == 80
     assert ctypes.sizeof(_lib.TallyItem) == 3 * 8 + 6 * 4
     assert _lib.TallyItem.max_unique.offset == 44
+    assert ctypes.sizeof(_lib.EncodeItem) == 5 * 8 + 4 * 4

@@ -273,3 +273,41 @@ def test_break_point_tables_match_reference(fixtures):
     table, lens = break_table(6, n_intervals=3)   # fixed number of intervals (mcmc.py:214-217)
     assert list(lens[1:]) == [3] * 6
     np.testing.assert_array_equal(table[4, :3], [0.0, 0.0, 1.0])
+
+
+# ----------------------------------------------------------------------------- read encoding (N2)
+def encode_names(fx):
+    return ["encode%d" % i for i in range(int(fx["n_encode"]))]
+
+
+def test_call_probabilities_match_reference(fixtures):
+    from mchap_b200.encoding import call_probabilities
+
+    for name in encode_names(fixtures):
+        got = call_probabilities(fixtures[name + "_calls"], fixtures[name + "_quals"], float(fixtures[name + "_error_rate"]))
+        np.testing.assert_array_equal(got, fixtures[name + "_probs"])
+
+
+@pytest.mark.gpu
+def test_device_read_encoding_matches_reference(fixtures):
+    """mchb_encode_reads_batch: as_probabilistic + unique_counts, byte for byte (NaN gaps included),
+    unique reads in the reference's first-occurrence order; all cases in one call."""
+    from mchap_b200.encoding import encode_unique_reads_batch
+
+    names = encode_names(fixtures)
+    out = encode_unique_reads_batch(
+        [fixtures[n + "_calls"] for n in names], [fixtures[n + "_probs"] for n in names],
+        [fixtures[n + "_n_alleles"] for n in names])
+    n_dup = 0
+    for name, (reads, counts) in zip(names, out):
+        want_r, want_c = fixtures[name + "_unique"], fixtures[name + "_counts"]
+        assert reads.shape == want_r.shape, name
+        assert reads.tobytes() == np.ascontiguousarray(want_r).tobytes(), name
+        np.testing.assert_array_equal(counts, want_c)
+        n_dup += int((want_c > 1).sum())
+    assert n_dup > 0
+    # a different error factor and scalar probabilities
+    calls = fixtures["encode2_calls"]
+    (reads, counts), = encode_unique_reads_batch([calls], [0.9], [fixtures["encode2_n_alleles"]], error_factor=2)
+    assert np.nanmax(reads) == 0.9 and np.isclose(np.nanmin(reads[reads > 0]), 0.05)
+    assert counts.sum() == len(calls)
