@@ -353,6 +353,26 @@ int mchb_encode_reads_batch(mchb_handle *h, int mem, const mchb_encode_item *ite
                             double error_factor, double *out_reads, int64_t out_reads_len,
                             int64_t *out_counts, int64_t out_counts_len, mchb_item_result *results);
 
+/* The whole per-sample device path of mchap/application/assemble.py:95-170 for a batch, one call:
+ * mchb_encode_reads_batch -> mchb_assemble_batch -> mchb_trace_tally_batch with every intermediate
+ * (encoded unique reads, counts, traces) kept in the handle's scratch on the device.  HOST memory
+ * in (calls, probs, n_alleles) and out (tallies).  assemble_items[i] carries ploidy, temperatures,
+ * seed, inbreeding, genotypes_off / llks_off (into the scratch trace) and initial_off = -1; its
+ * reads_off / counts_off / nalleles_off / n_reads / n_pos / max_allele are filled in by the library
+ * from encode_items[i] and the number of distinct reads.  tally_items as in
+ * mchb_assemble_tally_batch.  encode_results[i].n_het = distinct reads of item i. */
+int mchb_encode_assemble_tally_batch(mchb_handle *h, const mchb_assemble_params *params,
+                                     const mchb_encode_item *encode_items,
+                                     const mchb_assemble_item *assemble_items,
+                                     const mchb_tally_item *tally_items, int64_t n_items,
+                                     const int8_t *calls, int64_t calls_len, const double *probs,
+                                     int64_t probs_len, const int8_t *n_alleles, int64_t n_alleles_len,
+                                     double error_factor, int64_t genotypes_len, int64_t llks_len,
+                                     int8_t *out_states, int64_t out_states_len, int32_t *out_counts,
+                                     int32_t *out_first, int64_t tallies_len,
+                                     mchb_item_result *encode_results, mchb_item_result *results,
+                                     mchb_item_result *tally_results);
+
 #ifdef __cplusplus
 }
 #endif

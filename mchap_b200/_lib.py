@@ -182,7 +182,7 @@ SYMBOLS = [
     "mchb_assemble_batch", "mchb_measure_fp64_peak", "mchb_call_exact_mode_batch",
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
     "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
-    "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch",
+    "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch", "mchb_encode_assemble_tally_batch",
 ]
 
 
@@ -274,6 +274,11 @@ def load():
         L.mchb_encode_reads_batch.argtypes = [
             vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_double, vp, C.c_int64,
             vp, C.c_int64, vp,
+        ]
+        L.mchb_encode_assemble_tally_batch.restype = C.c_int
+        L.mchb_encode_assemble_tally_batch.argtypes = [
+            vp, C.POINTER(AssembleParams), vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
+            C.c_double, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp,
         ]
         _lib = L
         return _lib

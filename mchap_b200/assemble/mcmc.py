@@ -9,8 +9,10 @@ from dataclasses import dataclass
 import numpy as np
 
 from .. import _lib as L
-from ..api import (ASSEMBLE_ITEM_DTYPE, TALLY_ITEM_DTYPE, default_device, make_assemble_params,
-                   raise_item_status)
+import ctypes as C
+
+from ..api import (ASSEMBLE_ITEM_DTYPE, ITEM_RESULT_DTYPE, TALLY_ITEM_DTYPE, _ptr, default_device,
+                   make_assemble_params, raise_item_status)
 from .._lib import ITEM_TALLY_OVERFLOW as TALLY_OVERFLOW
 from .classes import GenotypeMultiTrace, TraceTally
 
@@ -181,24 +183,9 @@ class DenovoMCMC(object):
             return out, results
         return out
 
-    def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None,
-                            n_alleles_list=None, seeds=None, max_unique=128):
-        """``fit(...).burn(burn)`` for many items with the traces kept on the device: returns one
-        TraceTally per item (``.posterior()``, ``.split()``, ``.replicate_incongruence()`` behave
-        like the burnt GenotypeMultiTrace of the reference, mchap/application/assemble.py:123-170).
-
-        Only the tallies (distinct genotypes, counts and first occurrences per chain) cross the
-        bus.  Items with more than ``max_unique`` distinct genotypes are tallied a second time from
-        the trace still held on the device, with a table as large as the trace."""
-        dev = self.device or default_device()
-        n = len(reads_list)
-        burn = int(burn)
-        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds)
-        items = pk["items"]
-        params, keep = self._params(pk["nmax"])
-        kept = max(self.steps - max(burn, 0), 0) * self.chains
-        out = [None] * n
-
+    def _tally_helpers(self, items, burn, n, out):
+        """Closures shared by the fit_posterior_* methods: tally descriptors / output arrays for a set of
+        items, and the unpacking of the device tallies into TraceTally objects (returns the overflowed)."""
         def tally_items(idx, table):
             t = np.zeros(len(idx), dtype=TALLY_ITEM_DTYPE)
             pn = items["ploidy"][idx].astype(np.int64) * items["n_pos"][idx].astype(np.int64)
@@ -227,6 +214,28 @@ class DenovoMCMC(object):
                     first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64))
             return over
 
+        return tally_items, collect
+
+    def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None,
+                            n_alleles_list=None, seeds=None, max_unique=128):
+        """``fit(...).burn(burn)`` for many items with the traces kept on the device: returns one
+        TraceTally per item (``.posterior()``, ``.split()``, ``.replicate_incongruence()`` behave
+        like the burnt GenotypeMultiTrace of the reference, mchap/application/assemble.py:123-170).
+
+        Only the tallies (distinct genotypes, counts and first occurrences per chain) cross the
+        bus.  Items with more than ``max_unique`` distinct genotypes are tallied a second time from
+        the trace still held on the device, with a table as large as the trace."""
+        dev = self.device or default_device()
+        n = len(reads_list)
+        burn = int(burn)
+        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds)
+        items = pk["items"]
+        params, keep = self._params(pk["nmax"])
+        kept = max(self.steps - max(burn, 0), 0) * self.chains
+        out = [None] * n
+
+        tally_items, collect = self._tally_helpers(items, burn, n, out)
+
         everything = np.arange(n)
         table = max(1, min(int(max_unique), max(kept, 1)))
         t, states, counts, first = tally_items(everything, table)
@@ -249,3 +258,85 @@ class DenovoMCMC(object):
             for i, tr in zip(over, traces):
                 out[i] = TraceTally.from_trace(tr.burn(burn))
         return out
+
+    def fit_posterior_from_calls_batch(self, calls_list, probs_list, burn=0, n_alleles_list=None, seeds=None,
+                                       max_unique=128, error_factor=3):
+        """The whole per-sample device path in one call: integer allele calls + P(call correct)
+        (mchap/application/baseclass.py:194-209 encodes and de-duplicates them on the host) ->
+        de novo assembly -> tallies of the burnt trace.  Equivalent to
+        ``encode_unique_reads_batch`` followed by ``fit_posterior_batch``; the encoded reads and the
+        traces never leave the device.  Returns (tallies, n_unique_reads)."""
+        from ..encoding import ENCODE_ITEM_DTYPE, encode_unique_reads_batch
+
+        dev = self.device or default_device()
+        n = len(calls_list)
+        burn = int(burn)
+        temps = self._temperatures()
+        enc = np.zeros(n, dtype=ENCODE_ITEM_DTYPE)
+        items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
+        cs, ps, ns = [], [], []
+        co = no = ro = uo = go = lo = 0
+        nmax = 1
+        seed0 = self._seed()
+        for i in range(n):
+            c = np.ascontiguousarray(calls_list[i], dtype=np.int8)
+            assert c.ndim == 2
+            R, N = c.shape
+            p = np.ascontiguousarray(np.broadcast_to(np.asarray(probs_list[i], dtype=np.float64), (R, N)))
+            na = np.ascontiguousarray(self.n_alleles if n_alleles_list is None else n_alleles_list[i], dtype=np.int8)
+            assert len(na) == N
+            A = int(na.max()) if N > 0 else 0
+            nmax = max(nmax, N)
+            enc[i] = (co, co, no, ro, uo, R, N, A, 0)
+            it = items[i]
+            it["genotypes_off"], it["llks_off"] = go, lo
+            it["n_pos"], it["max_allele"], it["ploidy"] = N, max(A, 1), self.ploidy
+            it["temps_off"], it["n_temps"] = 0, len(temps)
+            it["seed"] = seed0 if seeds is None else int(seeds[i]) & 0xFFFFFFFF
+            it["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
+            it["initial_off"] = -1
+            cs.append(c.ravel())
+            ps.append(p.ravel())
+            ns.append(na)
+            co += R * N
+            no += N
+            ro += R * N * A
+            uo += R
+            go += self.chains * self.steps * self.ploidy * N
+            lo += self.chains * self.steps
+        calls = np.concatenate(cs) if cs else np.zeros(0, dtype=np.int8)
+        probs = np.concatenate(ps) if ps else np.zeros(0)
+        nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
+        params, keep = self._params(nmax)
+        kept = max(self.steps - max(burn, 0), 0) * self.chains
+        out = [None] * n
+        tally_items, collect = self._tally_helpers(items, burn, n, out)
+        everything = np.arange(n)
+        table = max(1, min(int(max_unique), max(kept, 1)))
+        t, states, counts, first = tally_items(everything, table)
+        eres = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        tres = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
+        rc = dev._lib.mchb_encode_assemble_tally_batch(
+            dev._h, C.byref(params), _ptr(enc), _ptr(items), _ptr(t), n, _ptr(calls), calls.size, _ptr(probs),
+            probs.size, _ptr(nall), nall.size, float(error_factor), go, lo, _ptr(states), states.size, _ptr(counts),
+            _ptr(first), counts.size, _ptr(eres), _ptr(results), _ptr(tres))
+        dev._check(rc)
+        for i in range(n):
+            raise_item_status(int(eres["status"][i]), i if n > 1 else None)
+            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+        over = collect(everything, t, tres, states, counts, first)
+        if over and kept <= 8192:
+            idx = np.array(over)
+            t, states, counts, first = tally_items(idx, kept)
+            tres = dev.trace_tally_call(t, None, 0, states, counts, first, mem_in=L.MEM_LAST_TRACE)
+            over = collect(idx, t, tres, states, counts, first)
+        if over:
+            pairs = encode_unique_reads_batch(sub2(calls_list, over), sub2(probs_list, over),
+                                              [self.n_alleles] * len(over) if n_alleles_list is None
+                                              else sub2(n_alleles_list, over), error_factor, dev)
+            traces = self.fit_batch([r for r, _ in pairs], [c for _, c in pairs], None, sub2(n_alleles_list, over),
+                                    sub2(seeds, over))
+            for i, tr in zip(over, traces):
+                out[i] = TraceTally.from_trace(tr.burn(burn))
+        return out, eres["n_het"].astype(np.int64)

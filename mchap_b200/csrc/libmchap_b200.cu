@@ -1600,3 +1600,86 @@ extern "C" int mchb_encode_reads_batch(mchb_handle *h, int mem, const mchb_encod
     h->kernel_ms += ms;
     return MCHB_OK;
 }
+
+extern "C" int mchb_encode_assemble_tally_batch(mchb_handle *h, const mchb_assemble_params *params,
+                                                const mchb_encode_item *encode_items,
+                                                const mchb_assemble_item *assemble_items,
+                                                const mchb_tally_item *tally_items, int64_t n_items,
+                                                const int8_t *calls, int64_t calls_len, const double *probs,
+                                                int64_t probs_len, const int8_t *n_alleles, int64_t n_alleles_len,
+                                                double error_factor, int64_t genotypes_len, int64_t llks_len,
+                                                int8_t *out_states, int64_t out_states_len, int32_t *out_counts,
+                                                int32_t *out_first, int64_t tallies_len,
+                                                mchb_item_result *encode_results, mchb_item_result *results,
+                                                mchb_item_result *tally_results) {
+    if (!h || !params || !encode_items || !assemble_items || !tally_items || !encode_results || !results ||
+        !tally_results || n_items < 0 || !out_states || !out_counts || !out_first || genotypes_len < 0 || llks_len < 0)
+        return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    // ---- inputs to the device; encoded reads and counts in scratch (capacity: one row per read)
+    int64_t reads_len = 0, counts_len = 0;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_encode_item &e = encode_items[i];
+        if (e.n_reads < 0 || e.n_pos < 0 || e.max_allele < 0 || e.reads_off < 0 || e.counts_off < 0) {
+            h->err = "bad encode item " + std::to_string(i);
+            return MCHB_ERR_ARGUMENT;
+        }
+        reads_len = std::max(reads_len, e.reads_off + (int64_t)e.n_reads * e.n_pos * e.max_allele);
+        counts_len = std::max(counts_len, e.counts_off + (int64_t)e.n_reads);
+    }
+    int rc;
+    const int8_t *dcalls, *dnall;
+    const double *dprobs;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_ECALLS, calls, calls_len, &dcalls))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_EPROBS, probs, probs_len, &dprobs))) return rc;
+    if ((rc = stage_in(h, MCHB_MEM_HOST, S_ENALL, n_alleles, n_alleles_len, &dnall))) return rc;
+    void *dreads, *dcounts, *dog, *dol;
+    if ((rc = ensure(h, S_EREADS, sizeof(double) * (size_t)std::max<int64_t>(reads_len, 1), &dreads))) return rc;
+    if ((rc = ensure(h, S_ECOUNTS, sizeof(int64_t) * (size_t)std::max<int64_t>(counts_len, 1), &dcounts))) return rc;
+    if ((rc = ensure(h, S_OUT_G, (size_t)std::max<int64_t>(genotypes_len, 1), &dog))) return rc;
+    if ((rc = ensure(h, S_OUT_L, sizeof(double) * (size_t)std::max<int64_t>(llks_len, 1), &dol))) return rc;
+    rc = mchb_encode_reads_batch(h, MCHB_MEM_DEVICE, encode_items, n_items, dcalls, calls_len, dprobs, probs_len, dnall,
+                                 n_alleles_len, error_factor, (double *)dreads, reads_len, (int64_t *)dcounts,
+                                 counts_len, encode_results);
+    if (rc) return rc;
+    float total_ms = h->kernel_ms;
+    int32_t total_launches = h->launches;
+    // ---- the samplers read the distinct reads where the encoder left them
+    std::vector<mchb_assemble_item> aitems(assemble_items, assemble_items + n_items);
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_encode_item &e = encode_items[i];
+        mchb_assemble_item &it = aitems[(size_t)i];
+        it.reads_off = e.reads_off;
+        it.counts_off = e.counts_off;
+        it.nalleles_off = e.nalleles_off;
+        it.initial_off = -1;
+        it.n_reads = encode_results[i].n_het;
+        it.n_pos = e.n_pos;
+        it.max_allele = std::max(e.max_allele, 1);
+        if (tally_items[i].genotypes_off != it.genotypes_off || tally_items[i].n_pos != it.n_pos ||
+            tally_items[i].ploidy != it.ploidy || tally_items[i].chains != params->chains ||
+            tally_items[i].steps != params->steps) {
+            h->err = "tally item " + std::to_string(i) + " does not describe the trace of assemble item " + std::to_string(i);
+            return MCHB_ERR_ARGUMENT;
+        }
+    }
+    rc = mchb_assemble_batch(h, MCHB_MEM_DEVICE, params, aitems.data(), n_items, (const double *)dreads, reads_len,
+                             (const int64_t *)dcounts, counts_len, dnall, n_alleles_len, nullptr, 0, (int8_t *)dog,
+                             genotypes_len, (double *)dol, llks_len, results);
+    if (rc) return rc;
+    h->last_trace_len = genotypes_len;
+    total_ms += h->kernel_ms;
+    total_launches += h->launches;
+    std::vector<mchb_tally_item> titems(tally_items, tally_items + n_items);
+    for (int64_t i = 0; i < n_items; i++)
+        if (results[i].status != MCHB_ITEM_OK) titems[(size_t)i].steps = 0;
+    h->kernel_ms = 0.f;
+    h->launches = 0;
+    rc = tally_run(h, 1, MCHB_MEM_DEVICE, MCHB_MEM_HOST, titems.data(), n_items, (const int8_t *)dog, genotypes_len,
+                   out_states, out_states_len, out_counts, out_first, tallies_len, tally_results);
+    h->kernel_ms += total_ms;
+    h->launches += total_launches;
+    return rc;
+}

@@ -311,3 +311,27 @@ def test_device_read_encoding_matches_reference(fixtures):
     (reads, counts), = encode_unique_reads_batch([calls], [0.9], [fixtures["encode2_n_alleles"]], error_factor=2)
     assert np.nanmax(reads) == 0.9 and np.isclose(np.nanmin(reads[reads > 0]), 0.05)
     assert counts.sum() == len(calls)
+
+
+@pytest.mark.gpu
+def test_chained_device_path_matches_the_separate_calls(fixtures):
+    """calls + probabilities -> encoded unique reads -> de novo assembly -> tallies in ONE call, with
+    the intermediates kept on the device == the three calls with host arrays in between."""
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.encoding import encode_unique_reads_batch
+
+    names = [n for n in encode_names(fixtures) if fixtures[n + "_calls"].shape[0] > 0 and
+             fixtures[n + "_unique"].shape[0] <= 256]
+    assert len(names) >= 5
+    calls = [fixtures[n + "_calls"] for n in names]
+    probs = [fixtures[n + "_probs"] for n in names]
+    nalls = [fixtures[n + "_n_alleles"] for n in names]
+    model = DenovoMCMC(ploidy=4, n_alleles=None, steps=120, chains=2, random_seed=17)
+    pairs = encode_unique_reads_batch(calls, probs, nalls)
+    want = model.fit_posterior_batch([r for r, _ in pairs], [c for _, c in pairs], burn=40, n_alleles_list=nalls)
+    got, n_unique = model.fit_posterior_from_calls_batch(calls, probs, burn=40, n_alleles_list=nalls)
+    for i, name in enumerate(names):
+        assert n_unique[i] == len(pairs[i][0]) == len(fixtures[name + "_unique"])
+        np.testing.assert_array_equal(got[i].states, want[i].states, err_msg=name)
+        np.testing.assert_array_equal(got[i].counts, want[i].counts)
+        np.testing.assert_array_equal(got[i].first, want[i].first)
