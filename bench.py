@@ -20,6 +20,7 @@ it: traces kept in HBM, tallies of the burnt trace returned) and call_exact (gen
 likelihoods/s of configs[2]).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -383,6 +384,51 @@ def run_b200(args, rank, world):
                     "trace (distinct genotypes, counts and first occurrences per chain) to the host",
         }
 
+    # ---- the whole per-sample device path: raw allele calls in (9 bytes per base), tallies out
+    # (mchb_encode_assemble_tally_batch: read encoding + de-duplication, de novo assembly, tallies)
+    from_calls = None
+    if posterior is not None and getattr(b, "calls", None) is not None:
+        from mchap_b200.encoding import ENCODE_ITEM_DTYPE
+
+        n_it = len(items)
+        calls = np.ascontiguousarray(b.calls).reshape(-1)
+        probs = np.full(calls.size, 1 - 0.0024)          # io/bam.py:281: error rate only, no base qualities
+        enc = np.zeros(n_it, dtype=ENCODE_ITEM_DTYPE)
+        idx = np.arange(n_it, dtype=np.int64)
+        enc["calls_off"] = enc["probs_off"] = idx * DEPTH * N_POS
+        enc["nalleles_off"] = idx * N_POS
+        enc["reads_off"] = idx * DEPTH * N_POS * 2
+        enc["counts_off"] = idx * DEPTH
+        enc["n_reads"], enc["n_pos"], enc["max_allele"] = DEPTH, N_POS, 2
+        eres = np.zeros(n_it, dtype=tres.dtype)
+        ares = np.zeros(n_it, dtype=tres.dtype)
+        tres2 = np.zeros(n_it, dtype=tres.dtype)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def calls_step():
+            rc = dev._lib.mchb_encode_assemble_tally_batch(
+                dev._h, C.byref(params), ptr(enc), ptr(items), ptr(titems), n_it, ptr(calls), calls.size, ptr(probs),
+                probs.size, ptr(h_nall.numpy()), h_nall.numel(), 3.0, g_len, l_len, ptr(o_states), o_states.size,
+                ptr(o_counts), ptr(o_first), o_counts.size, ptr(eres), ptr(ares), ptr(tres2))
+            dev._check(rc)
+
+        want_states, want_counts = o_states.copy(), o_counts.copy()   # from the e2e_posterior runs above
+        calls_step()
+        same = bool(np.array_equal(o_states, want_states) and np.array_equal(o_counts, want_counts) and
+                    np.array_equal(eres["n_het"], b.n_reads()))
+        t0 = time.perf_counter()
+        for _ in range(n_post):
+            calls_step()
+        dt = time.perf_counter() - t0
+        from_calls = {
+            "value": n_post * items_per_step * CHAINS * MCMC_STEPS / dt, "unit": UNIT, "steps": n_post,
+            "ms_per_step": 1e3 * dt / n_post, "kernel_ms_per_step": dev.last_kernel_ms,
+            "h2d_bytes_per_step": int(calls.nbytes + probs.nbytes + h_nall.numel() + enc.nbytes + items.nbytes),
+            "same_tallies_as_e2e_posterior": same,
+            "note": "mchb_encode_assemble_tally_batch: raw fragments (int8 calls + P(correct)) in, read encoding + "
+                    "de-duplication, assembly and tallies on the device, tallies out",
+        }
+
     # ---- roofline of the dominant kernel (assemble_kernel): FP64 SIMT pipe
     main_items_per_launch = int(np.mean([(b.n_reads() <= 32).sum() for b, _ in batches]))
     peak_tf = dev.measure_fp64_peak()
@@ -432,7 +478,7 @@ def run_b200(args, rank, world):
                        "l2": "each step reads a different batch and writes a 9.6 GB trace (> L2)",
                        "mean_unique_reads": float(np.mean([b.n_reads().mean() for b, _ in batches]))},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "call_exact": call_exact, "e2e_posterior": posterior,
+            "call_exact": call_exact, "e2e_posterior": posterior, "e2e_from_calls": from_calls,
             "wall_ms_per_step": 1e3 * wall_max / K,
         }
         print(json.dumps(line), flush=True)

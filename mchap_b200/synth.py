@@ -137,4 +137,6 @@ def _synth_from_haplotypes(haps, depth, n_alleles, error_rate, rng, min_window=N
     reads = encode_calls(u_calls, n_all[item_of], A, error_rate)
     offsets = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(item_of, minlength=n), out=offsets[1:])
-    return ItemBatch(reads, cnt.astype(np.int64), offsets, n_all, haps.astype(np.int8), ploidy, N, A)
+    batch = ItemBatch(reads, cnt.astype(np.int64), offsets, n_all, haps.astype(np.int8), ploidy, N, A)
+    batch.calls = calls  # int8 [n_items, depth, n_pos]: the raw fragments before encoding / de-duplication
+    return batch
