@@ -1044,7 +1044,6 @@ struct AsmCtx {
                 return;
             }
         }
-        int my_return = 1;
         double my_la = -INFINITY;
 #pragma unroll 1
         for (int base = 0; base < n_options; base += 32) {
@@ -1081,14 +1080,12 @@ struct AsmCtx {
                 if (i < 32) {
                     if (lane == i) {
                         my_la = la;
-                        my_return = n_return;
                     }
                 }
                 oll()[i] = llk_i;
                 opr()[i] = la;
             }
         }
-        (void)my_return;
         double *ol = oll(), *op = opr();
         // all proposals hopeless (exp(la) < 2^-54 each) and u > 0: the cumulative sums stay below
         // u until the final "stay" slot, so the outcome is "stay" without evaluating exp()

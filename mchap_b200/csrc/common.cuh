@@ -98,26 +98,6 @@ struct WordStream {
     }
     // the double that the (off/2)-th next call of next_double() would return (off even, < 63)
     __device__ __forceinline__ double double_at(int off) const { return to_double(word_at(off), word_at(off + 1)); }
-    // randint(n) with the rejection loop resolved by one ballot: lane l looks at word cursor + l,
-    // the first lane whose masked word is below n wins and the cursor moves just past it (the
-    // words before it are exactly the ones the serial loop would have rejected).  Same values and
-    // same consumption as randint(); n <= 2^31.
-    __device__ __forceinline__ int randint_ballot(int n) {
-        if (n == 1) return 0;
-        const uint32_t mask = 0xffffffffu >> __clz(n - 1);
-        for (;;) {
-            const uint32_t r = word_at(lane) & mask;
-            const unsigned ok = __ballot_sync(MCHB_FULL, (int)r < n);
-            if (ok) {
-                const int f = __ffs(ok) - 1;
-                const int k = (int)__shfl_sync(MCHB_FULL, r, f);
-                advance(f + 1);
-                return k;
-            }
-            advance(32);  // 32 rejections in a row (probability < 2^-32) or the end of the stream
-            if (cur > len + 64) return 0;
-        }
-    }
     // randomimpl.py:454-520 _randrange_impl (state "np", n <= 2^31 here); n == 1 draws nothing.
     // Past the end of the stream the words are 0, which ends the rejection loop.
     __device__ __forceinline__ int randint(int n) {
