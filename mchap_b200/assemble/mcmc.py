@@ -94,49 +94,51 @@ class DenovoMCMC(object):
         """Flat input arrays + item descriptors of a batch (outputs laid out item after item)."""
         n = len(reads_list)
         temps = self._temperatures()
-        items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
-        rs, cs, ns, ins = [], [], [], []
-        ro = co = no = io = go = lo = 0
         use_counts = counts_list is not None and any(c is not None for c in counts_list)
         use_initial = initial_list is not None and any(i is not None for i in initial_list)
         seed0 = self._seed()
-        shapes = []
-        nmax = 1
+        default_na = None if n_alleles_list is not None else np.ascontiguousarray(self.n_alleles, dtype=np.int8)
+        rs, cs, ns, ins = [], [], [], []
+        Us, Ns, As = [0] * n, [0] * n, [0] * n          # per-item scalars, assigned column-wise below
+        init_off, init_nhet = [-1] * n, [0] * n
+        io = 0
         for i in range(n):
             r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
             assert r.ndim == 3
             U, N, A = r.shape
-            na = np.ascontiguousarray(self.n_alleles if n_alleles_list is None else n_alleles_list[i], dtype=np.int8)
+            na = default_na if default_na is not None else np.ascontiguousarray(n_alleles_list[i], dtype=np.int8)
             assert len(na) == N
-            nmax = max(nmax, N)
-            it = items[i]
-            it["reads_off"], it["counts_off"], it["nalleles_off"] = ro, co, no
-            it["genotypes_off"], it["llks_off"] = go, lo
-            it["n_reads"], it["n_pos"], it["max_allele"], it["ploidy"] = U, N, max(A, 1), self.ploidy
-            it["temps_off"], it["n_temps"] = 0, len(temps)
-            it["seed"] = seed0 if seeds is None else int(seeds[i]) & 0xFFFFFFFF
-            it["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
-            it["initial_off"] = -1
+            Us[i], Ns[i], As[i] = U, N, A
             if use_initial and initial_list[i] is not None:
                 ini = np.ascontiguousarray(initial_list[i], dtype=np.int8)
                 assert ini.ndim == 3 and ini.shape[0] == self.chains and ini.shape[1] == self.ploidy
-                it["initial_off"] = io
-                it["initial_nhet"] = ini.shape[2]
+                init_off[i], init_nhet[i] = io, ini.shape[2]
                 ins.append(ini.ravel())
                 io += ini.size
-            rs.append(r.ravel())
+            rs.append(r.reshape(-1))
             ns.append(na)
-            ro += r.size
-            no += N
             if use_counts:
                 c = counts_list[i]
                 c = np.ones(U, dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64)
                 assert len(c) == U or U == 0
                 cs.append(c[:U])
-                co += U
-            shapes.append((N, go, lo))
-            go += self.chains * self.steps * self.ploidy * N
-            lo += self.chains * self.steps
+        U_, N_, A_ = (np.asarray(x, dtype=np.int64) for x in (Us, Ns, As))
+        excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        g_sizes = self.chains * self.steps * self.ploidy * N_
+        l_sizes = np.full(n, self.chains * self.steps, dtype=np.int64)
+        items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
+        items["reads_off"] = excl(U_ * N_ * A_)
+        items["counts_off"] = excl(U_) if use_counts else 0
+        items["nalleles_off"] = excl(N_)
+        items["genotypes_off"], items["llks_off"] = excl(g_sizes), excl(l_sizes)
+        items["n_reads"], items["n_pos"], items["max_allele"], items["ploidy"] = U_, N_, np.maximum(A_, 1), self.ploidy
+        items["temps_off"], items["n_temps"] = 0, len(temps)
+        items["seed"] = seed0 if seeds is None else (np.asarray(seeds, dtype=np.uint64) & 0xFFFFFFFF).astype(np.uint32)
+        items["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
+        items["initial_off"], items["initial_nhet"] = init_off, init_nhet
+        go, lo = int(g_sizes.sum()), int(l_sizes.sum())
+        shapes = list(zip(Ns, items["genotypes_off"].tolist(), items["llks_off"].tolist()))
+        nmax = max(Ns + [1])
         reads = np.concatenate(rs) if rs else np.zeros(0)
         nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
         counts = np.concatenate(cs) if use_counts and cs else None
