@@ -321,55 +321,53 @@ class CallBatch:
     def __init__(self, reads_list, haplotypes_list, ploidy, counts_list=None, priors=None):
         n = len(reads_list)
         self.n = n
-        items = np.zeros(n, dtype=CALL_ITEM_DTYPE)
         ploidies = np.broadcast_to(np.asarray(ploidy, dtype=np.int64), (n,))
         rs, hs, cs, fs = [], [], [], []
-        ro = ho = co = fo = oo = go = 0
         use_counts = counts_list is not None and any(c is not None for c in counts_list)
-        self.n_genotypes = np.zeros(n, dtype=np.int64)
+        Us, Ns, As, Hs = [0] * n, [0] * n, [0] * n, [0] * n   # per-item scalars, assigned column-wise below
+        inbs, foffs = [np.nan] * n, [-1] * n
+        fo = 0
         for i in range(n):
             r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
             hp = np.ascontiguousarray(haplotypes_list[i], dtype=np.int8)
             assert r.ndim == 3 and hp.ndim == 2 and hp.shape[1] == r.shape[1]
-            U, N, A = r.shape
-            H = hp.shape[0]
-            P = int(ploidies[i])
+            Us[i], Ns[i], As[i] = r.shape
+            H = Hs[i] = hp.shape[0]
             prior = None if priors is None else priors[i]
-            it = items[i]
-            it["reads_off"], it["counts_off"], it["haps_off"] = ro, co, ho
-            it["hap_out_off"], it["gl_off"] = oo, go
-            it["n_reads"], it["n_pos"], it["max_allele"], it["ploidy"], it["n_haps"] = U, N, A, P, H
-            it["freqs_off"] = -1
-            it["inbreeding"] = np.nan
             if prior is not None:
                 inb, fr = prior
-                it["inbreeding"] = float(inb)
+                inbs[i] = float(inb)
                 if fr is not None:
                     fr = np.ascontiguousarray(fr, dtype=np.float64)
                     assert len(fr) == H
-                    it["freqs_off"] = fo
+                    foffs[i] = fo
                     fs.append(fr)
                     fo += H
-            G = count_genotypes(H, P)
-            self.n_genotypes[i] = G
-            rs.append(r.ravel())
-            hs.append(hp.ravel())
-            ro += r.size
-            ho += hp.size
-            oo += H
-            go += G
+            rs.append(r.reshape(-1))
+            hs.append(hp.reshape(-1))
             if use_counts:
                 c = counts_list[i]
-                c = np.ones(U, dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64)
-                cs.append(c)
-                co += U
+                cs.append(np.ones(Us[i], dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64))
+        U_, N_, A_, H_ = (np.asarray(x, dtype=np.int64) for x in (Us, Ns, As, Hs))
+        excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        memo = {}
+        self.n_genotypes = np.array(
+            [memo.setdefault(k, count_genotypes(*k)) for k in zip(Hs, ploidies.tolist())], dtype=np.int64)
+        items = np.zeros(n, dtype=CALL_ITEM_DTYPE)
+        items["reads_off"] = excl(U_ * N_ * A_)
+        items["counts_off"] = excl(U_) if use_counts else 0
+        items["haps_off"] = excl(H_ * N_)
+        items["hap_out_off"], items["gl_off"] = excl(H_), excl(self.n_genotypes)
+        items["n_reads"], items["n_pos"], items["max_allele"], items["n_haps"] = U_, N_, A_, H_
+        items["ploidy"] = ploidies
+        items["freqs_off"], items["inbreeding"] = foffs, inbs
         self.items = items
         self.reads = np.concatenate(rs) if rs else np.zeros(0)
         self.haps = np.concatenate(hs) if hs else np.zeros(0, dtype=np.int8)
         self.counts = np.concatenate(cs) if use_counts else None
         self.freqs = np.concatenate(fs) if fs else None
-        self.hap_total = oo
-        self.gl_total = go
+        self.hap_total = int(H_.sum())
+        self.gl_total = int(self.n_genotypes.sum())
         self.pmax = int(ploidies.max()) if n else 1
 
 
