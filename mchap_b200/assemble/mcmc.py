@@ -274,38 +274,38 @@ class DenovoMCMC(object):
         n = len(calls_list)
         burn = int(burn)
         temps = self._temperatures()
-        enc = np.zeros(n, dtype=ENCODE_ITEM_DTYPE)
-        items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
         cs, ps, ns = [], [], []
-        co = no = ro = uo = go = lo = 0
-        nmax = 1
-        seed0 = self._seed()
+        Rs, Ns, As = [0] * n, [0] * n, [0] * n
+        default_na = None if n_alleles_list is not None else np.ascontiguousarray(self.n_alleles, dtype=np.int8)
         for i in range(n):
             c = np.ascontiguousarray(calls_list[i], dtype=np.int8)
             assert c.ndim == 2
             R, N = c.shape
             p = np.ascontiguousarray(np.broadcast_to(np.asarray(probs_list[i], dtype=np.float64), (R, N)))
-            na = np.ascontiguousarray(self.n_alleles if n_alleles_list is None else n_alleles_list[i], dtype=np.int8)
+            na = default_na if default_na is not None else np.ascontiguousarray(n_alleles_list[i], dtype=np.int8)
             assert len(na) == N
-            A = int(na.max()) if N > 0 else 0
-            nmax = max(nmax, N)
-            enc[i] = (co, co, no, ro, uo, R, N, A, 0)
-            it = items[i]
-            it["genotypes_off"], it["llks_off"] = go, lo
-            it["n_pos"], it["max_allele"], it["ploidy"] = N, max(A, 1), self.ploidy
-            it["temps_off"], it["n_temps"] = 0, len(temps)
-            it["seed"] = seed0 if seeds is None else int(seeds[i]) & 0xFFFFFFFF
-            it["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
-            it["initial_off"] = -1
-            cs.append(c.ravel())
-            ps.append(p.ravel())
+            Rs[i], Ns[i], As[i] = R, N, (int(na.max()) if N > 0 else 0)
+            cs.append(c.reshape(-1))
+            ps.append(p.reshape(-1))
             ns.append(na)
-            co += R * N
-            no += N
-            ro += R * N * A
-            uo += R
-            go += self.chains * self.steps * self.ploidy * N
-            lo += self.chains * self.steps
+        R_, N_, A_ = (np.asarray(x, dtype=np.int64) for x in (Rs, Ns, As))
+        excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        enc = np.zeros(n, dtype=ENCODE_ITEM_DTYPE)
+        enc["calls_off"] = enc["probs_off"] = excl(R_ * N_)
+        enc["nalleles_off"] = excl(N_)
+        enc["reads_off"], enc["counts_off"] = excl(R_ * N_ * A_), excl(R_)
+        enc["n_reads"], enc["n_pos"], enc["max_allele"] = R_, N_, A_
+        items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
+        g_sizes = self.chains * self.steps * self.ploidy * N_
+        items["genotypes_off"] = excl(g_sizes)
+        items["llks_off"] = np.arange(n, dtype=np.int64) * (self.chains * self.steps)
+        items["n_pos"], items["max_allele"], items["ploidy"] = N_, np.maximum(A_, 1), self.ploidy
+        items["temps_off"], items["n_temps"] = 0, len(temps)
+        items["seed"] = self._seed() if seeds is None else (np.asarray(seeds, dtype=np.uint64) & 0xFFFFFFFF).astype(np.uint32)
+        items["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
+        items["initial_off"] = -1
+        go, lo = int(g_sizes.sum()), n * self.chains * self.steps
+        nmax = max(Ns + [1])
         calls = np.concatenate(cs) if cs else np.zeros(0, dtype=np.int8)
         probs = np.concatenate(ps) if ps else np.zeros(0)
         nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
