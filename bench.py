@@ -483,6 +483,7 @@ def run_b200(args, rank, world):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()  # rank 0 ran the secondary measurements alone: leave together
         dist.destroy_process_group()
 
 
