@@ -869,7 +869,7 @@ static double mutation_compound_step(asm_ctx *c, orc_rng *rng, int8_t *genotype,
 /* assemble/structural.py:23-71 random_breaks. out i64[(breaks+1)*2] */
 static int random_breaks(orc_rng *rng, int64_t breaks, int64_t n, int64_t *out)
 {
-    if (breaks >= n)
+    if (breaks >= n || n < 0)
         return ORC_ERR_BREAKS;
     uint8_t *ind = (uint8_t *)malloc((size_t)n + 1);
     int64_t *opts = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n + 1));
@@ -931,7 +931,7 @@ static void label_haplotypes(int8_t *labels /* stride 2 */, const int8_t *genoty
 void orc_haplotype_segment_labels(const int8_t *genotype, int P, int N, int has_interval,
                                   int start, int stop, int8_t *labels)
 {
-    int *cols = (int *)malloc(sizeof(int) * ((size_t)N + 1));
+    int *cols = (int *)calloc((size_t)N + 1, sizeof(int));
     int n = 0;
     if (!has_interval) {
         start = 0;
