@@ -373,6 +373,24 @@ int mchb_encode_assemble_tally_batch(mchb_handle *h, const mchb_assemble_params 
                                      mchb_item_result *encode_results, mchb_item_result *results,
                                      mchb_item_result *tally_results);
 
+/* ---- minimum error correction ------------------------------------------------------------
+ * Replaces: encoding/integer/stats.py:18-39 minimum_error_correction as the CLIs use it
+ * (application/assemble.py:158-163, call.py:170-175, call_exact.py:186-191): for every read the
+ * number of called positions (call >= 0) at which it differs from the closest haplotype of the
+ * called genotype.  Item i: calls int8[n_reads, n_pos] at calls + calls_off, genotype
+ * int8[ploidy, n_pos] at genotypes + geno_off.  out_mec[i] = sum over reads; out_called[i]
+ * (optional) = number of calls >= 0; out_per_read (optional) int32 rows at per_read_off. */
+typedef struct {
+    int64_t calls_off;       /* int8 elements */
+    int64_t geno_off;        /* int8 elements */
+    int64_t per_read_off;    /* int32 elements into out_per_read */
+    int32_t n_reads, n_pos, ploidy, reserved;
+} mchb_mec_item;
+
+int mchb_mec_batch(mchb_handle *h, int mem, const mchb_mec_item *items, int64_t n_items,
+                   const int8_t *calls, int64_t calls_len, const int8_t *genotypes, int64_t genotypes_len,
+                   int64_t *out_mec, int64_t *out_called, int32_t *out_per_read, int64_t per_read_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,18 @@ class EncodeItem(C.Structure):
     ]
 
 
+class MecItem(C.Structure):
+    _fields_ = [
+        ("calls_off", C.c_int64),
+        ("geno_off", C.c_int64),
+        ("per_read_off", C.c_int64),
+        ("n_reads", C.c_int32),
+        ("n_pos", C.c_int32),
+        ("ploidy", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 class CallMcmcParams(C.Structure):
     _fields_ = [
         ("steps", C.c_int32),
@@ -183,6 +195,7 @@ SYMBOLS = [
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
     "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
     "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch", "mchb_encode_assemble_tally_batch",
+    "mchb_mec_batch",
 ]
 
 
@@ -197,8 +210,8 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
-        if not os.path.exists(path):
-            _build.build()
+        if _build.needs_build() and (_build.have_nvcc() or not os.path.exists(path)):
+            _build.build()   # raises without nvcc: there is nothing else to run
         L = C.CDLL(path)
         vp = C.c_void_p
         L.mchb_create.restype = C.c_int
@@ -280,5 +293,7 @@ def load():
             vp, C.POINTER(AssembleParams), vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64,
             C.c_double, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp,
         ]
+        L.mchb_mec_batch.restype = C.c_int
+        L.mchb_mec_batch.argtypes = [vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, C.c_int64]
         _lib = L
         return _lib

@@ -14,6 +14,7 @@ LLK_ITEM_DTYPE = L._np_dtype(L.LlkItem)
 ITEM_RESULT_DTYPE = L._np_dtype(L.ItemResult)
 TALLY_ITEM_DTYPE = L._np_dtype(L.TallyItem)
 CALL_ITEM_DTYPE = L._np_dtype(L.CallItem)
+MEC_ITEM_DTYPE = L._np_dtype(L.MecItem)
 
 _ITEM_ERRORS = {
     L.ITEM_NAN_LLK: (ValueError, "Encountered log likelihood of nan"),
@@ -29,14 +30,21 @@ class MchapB200Error(RuntimeError):
     pass
 
 
-def raise_item_status(status, index=None):
-    """Re-raise a per-item device status with the reference's exception type and message."""
+def item_status_error(status, index=None):
+    """The exception a per-item device status stands for (reference's type and message), or None."""
     if status == L.ITEM_OK:
-        return
+        return None
     exc, msg = _ITEM_ERRORS.get(int(status), (MchapB200Error, "device status %d" % status))
     if index is not None:
         msg = "%s (item %d)" % (msg, index)
-    raise exc(msg)
+    return exc(msg)
+
+
+def raise_item_status(status, index=None):
+    """Re-raise a per-item device status with the reference's exception type and message."""
+    exc = item_status_error(status, index)
+    if exc is not None:
+        raise exc
 
 
 def _ptr(a):
@@ -132,6 +140,35 @@ class Device:
         out = np.empty((i.shape[0], int(ploidy)), dtype=np.int64)
         self._check(self._lib.mchb_genotype_unrank(self._h, L.MEM_HOST, _ptr(i), i.shape[0], int(ploidy), _ptr(out)))
         return out
+
+    # ------------------------------------------------------------------ MEC
+    def minimum_error_correction_batch(self, calls_list, genotypes_list, per_read=False):
+        """encoding/integer/stats.py:18-39 for many (read calls int[R, N], genotype int[P, N]) pairs:
+        returns (mec sums int64[n], called-base counts int64[n]) and, with per_read=True, the list of
+        per-read arrays the reference returns."""
+        n = len(calls_list)
+        cs = [np.ascontiguousarray(c, dtype=np.int8) for c in calls_list]
+        gs = [np.ascontiguousarray(g, dtype=np.int8) for g in genotypes_list]
+        items = np.zeros(n, dtype=MEC_ITEM_DTYPE)
+        R_ = np.array([c.shape[0] for c in cs], dtype=np.int64)
+        N_ = np.array([c.shape[1] for c in cs], dtype=np.int64)
+        P_ = np.array([g.shape[0] for g in gs], dtype=np.int64)
+        assert all(g.ndim == 2 and g.shape[1] == c.shape[1] for g, c in zip(gs, cs))
+        excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        items["calls_off"], items["geno_off"], items["per_read_off"] = excl(R_ * N_), excl(P_ * N_), excl(R_)
+        items["n_reads"], items["n_pos"], items["ploidy"] = R_, N_, P_
+        calls = np.concatenate(cs, axis=None) if n else np.zeros(0, dtype=np.int8)
+        genos = np.concatenate(gs, axis=None) if n else np.zeros(0, dtype=np.int8)
+        mec = np.zeros(n, dtype=np.int64)
+        called = np.zeros(n, dtype=np.int64)
+        rows = np.zeros(max(int(R_.sum()), 1), dtype=np.int32) if per_read else None
+        self._check(self._lib.mchb_mec_batch(
+            self._h, L.MEM_HOST, _ptr(items), n, _ptr(calls), calls.size, _ptr(genos), genos.size, _ptr(mec),
+            _ptr(called), _ptr(rows), int(R_.sum()) if per_read else 0))
+        if per_read:
+            offs = items["per_read_off"]
+            return mec, called, [rows[int(o): int(o) + int(r)].astype(np.int64) for o, r in zip(offs, R_)]
+        return mec, called
 
     # ------------------------------------------------------------------ K1
     def log_likelihood_batch(self, reads_list, genotypes_list, counts_list=None):

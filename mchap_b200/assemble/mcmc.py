@@ -1,18 +1,31 @@
 """``DenovoMCMC`` with the reference's constructor and ``fit`` signature
 (reference: mchap/assemble/mcmc.py:24-161), executed by the CUDA kernel ``assemble_kernel``.
 
-``fit`` handles one (locus, sample) item like the reference; ``fit_batch`` sends many items in
-one device call (the reason this package exists).  There is no CPU path.
+``fit`` handles one (locus, sample) item like the reference; the ``*_batch`` methods send many
+items in one device call (the reason this package exists).  There is no CPU path.
+
+Batch conventions shared by every ``*_batch`` method:
+
+* per-item overrides — ``n_alleles_list``, ``seeds``, ``ploidy_list``, ``inbreeding_list``
+  (``None`` entries = flat prior), ``temperatures_list`` — default to the model's own parameters
+  for every item, so that samples of different ploidy / prior / temperature ladder (pools, per-sample
+  CLI files) share one launch;
+* ``errors="raise"`` (default) re-raises the first per-item device status with the reference's
+  exception type; ``errors="return"`` puts the exception object in that item's slot of the result
+  list instead, so one bad item does not discard the finished results of the others.
+
+Limits of the CUDA kernels (``mchb_get_limits``; items outside them get ``NotImplementedError``, never
+an approximation): ploidy <= 16, variable positions x bits per allele <= 64, <= 256 distinct reads
+per item, <= 8 temperatures.
 """
+import ctypes as C
 from dataclasses import dataclass
 
 import numpy as np
 
 from .. import _lib as L
-import ctypes as C
-
 from ..api import (ASSEMBLE_ITEM_DTYPE, ITEM_RESULT_DTYPE, TALLY_ITEM_DTYPE, _ptr, default_device,
-                   make_assemble_params, raise_item_status)
+                   item_status_error, make_assemble_params)
 from .._lib import ITEM_TALLY_OVERFLOW as TALLY_OVERFLOW
 from .classes import GenotypeMultiTrace, TraceTally
 
@@ -30,8 +43,16 @@ def point_beta_probabilities(n_base, a=1.0, b=3.0):
     return cdf
 
 
+_BREAK_TABLES = {}
+
+
 def break_table(n_pos, alpha=1.0, beta=3.0, n_intervals=None):
-    """Row n = break-point distribution used when n positions stay variable (mcmc.py:211-217)."""
+    """Row n = break-point distribution used when n positions stay variable (mcmc.py:211-217).
+    Tables are memoised: the CLIs build the same one for every block of loci."""
+    key = (int(n_pos), float(alpha), float(beta), n_intervals)
+    hit = _BREAK_TABLES.get(key)
+    if hit is not None:
+        return hit
     stride = max(int(n_pos), int(n_intervals or 0), 1)
     table = np.zeros((n_pos + 1, stride), dtype=np.float64)
     lens = np.zeros(n_pos + 1, dtype=np.int32)
@@ -43,11 +64,50 @@ def break_table(n_pos, alpha=1.0, beta=3.0, n_intervals=None):
             row[-1] = 1
         table[n, : len(row)] = row
         lens[n] = len(row)
+    _BREAK_TABLES[key] = (table, lens)
     return table, lens
 
 
 def sub2(lst, idx):
     return None if lst is None else [lst[i] for i in idx]
+
+
+def _excl(x):
+    """Exclusive prefix sum (element offsets of back-to-back items)."""
+    x = np.asarray(x, dtype=np.int64)
+    out = np.zeros(len(x), dtype=np.int64)
+    if len(x) > 1:
+        np.cumsum(x[:-1], out=out[1:])
+    return out
+
+
+def _f64c(a):
+    if type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _flat(arrays, dtype):
+    return np.concatenate(arrays, axis=None) if len(arrays) else np.zeros(0, dtype=dtype)
+
+
+def _sort_temperatures(temperatures):
+    temps = np.sort(np.asarray(temperatures, dtype=np.float64).ravel())
+    assert temps[0] >= 0.0
+    assert temps[-1] == 1.0
+    return temps
+
+
+def _settle(out, i, status, n, errors):
+    """Handle the device status of item i: returns True when the item is fine; otherwise raises
+    (errors='raise') or stores the exception in out[i] (errors='return')."""
+    exc = item_status_error(int(status), i if n > 1 else None)
+    if exc is None:
+        return True
+    if errors == "raise":
+        raise exc
+    out[i] = exc
+    return False
 
 
 @dataclass
@@ -74,10 +134,7 @@ class DenovoMCMC(object):
         return cls(*args, **kwargs)
 
     def _temperatures(self):
-        temps = np.sort(np.asarray(self.temperatures, dtype=np.float64))
-        assert temps[0] >= 0.0
-        assert temps[-1] == 1.0
-        return temps
+        return _sort_temperatures(self.temperatures)
 
     def _seed(self):
         if self.random_seed is not None:
@@ -90,111 +147,151 @@ class DenovoMCMC(object):
         res = self.fit_batch([reads], [read_counts], None if initial is None else [initial])
         return res[0]
 
-    def _pack(self, reads_list, counts_list, initial_list, n_alleles_list, seeds):
-        """Flat input arrays + item descriptors of a batch (outputs laid out item after item)."""
+    # ------------------------------------------------------------------ packing
+    def _item_params(self, n, seeds, ploidy_list, inbreeding_list, temperatures_list):
+        """Per-item ploidy / inbreeding / temperature ladder / seed columns + the temperature pool."""
+        ploidy = (np.full(n, int(self.ploidy), dtype=np.int64) if ploidy_list is None
+                  else np.asarray(ploidy_list, dtype=np.int64).reshape(n))
+        if inbreeding_list is None:
+            inb = np.full(n, np.nan if self.inbreeding is None else float(self.inbreeding))
+        else:
+            inb = np.array([np.nan if v is None else float(v) for v in inbreeding_list], dtype=np.float64).reshape(n)
+        if temperatures_list is None:
+            pool = self._temperatures()
+            t_off = np.zeros(n, dtype=np.int64)
+            t_len = np.full(n, len(pool), dtype=np.int64)
+        else:
+            ladders, where, t_off, t_len, pos = [], {}, np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64), 0
+            for i, t in enumerate(temperatures_list):
+                key = tuple(np.asarray(self.temperatures if t is None else t, dtype=np.float64).ravel().tolist())
+                hit = where.get(key)
+                if hit is None:
+                    ladder = _sort_temperatures(key)
+                    hit = where[key] = (pos, len(ladder))
+                    ladders.append(ladder)
+                    pos += len(ladder)
+                t_off[i], t_len[i] = hit
+            pool = np.concatenate(ladders) if ladders else np.ones(1)
+        seed = (np.full(n, self._seed(), dtype=np.uint32) if seeds is None
+                else (np.asarray(seeds, dtype=np.uint64) & 0xFFFFFFFF).astype(np.uint32).reshape(n))
+        return ploidy, inb, pool, t_off, t_len, seed
+
+    def _pack(self, reads_list, counts_list, initial_list, n_alleles_list, seeds, ploidy_list=None,
+              inbreeding_list=None, temperatures_list=None):
+        """Flat input arrays + item descriptors of a batch (outputs laid out item after item).
+        Column-wise: per-item Python work is a handful of list comprehensions, the bulk arrays are
+        flattened and joined by one ``np.concatenate`` each."""
         n = len(reads_list)
-        temps = self._temperatures()
+        ploidy, inb, pool, t_off, t_len, seed = self._item_params(n, seeds, ploidy_list, inbreeding_list,
+                                                                  temperatures_list)
+        arrs = [_f64c(r) for r in reads_list]
+        assert all(a.ndim == 3 for a in arrs), "reads must be [n_reads, n_positions, max_allele] per item"
+        shp = np.array([a.shape for a in arrs], dtype=np.int64).reshape(n, 3)
+        U_, N_, A_ = shp[:, 0], shp[:, 1], shp[:, 2]
+        if n_alleles_list is None:
+            default_na = np.ascontiguousarray(self.n_alleles, dtype=np.int8)
+            assert n == 0 or (N_ == len(default_na)).all()
+            nall = np.tile(default_na, n)
+        else:
+            nas = [np.asarray(a, dtype=np.int8) for a in n_alleles_list]
+            assert [len(a) for a in nas] == N_.tolist()
+            nall = _flat(nas, np.int8)
         use_counts = counts_list is not None and any(c is not None for c in counts_list)
+        counts = None
+        if use_counts:
+            cs = [np.ones(u, dtype=np.int64) if c is None else np.asarray(c, dtype=np.int64)[:u]
+                  for c, u in zip(counts_list, U_.tolist())]
+            assert [len(c) for c in cs] == U_.tolist()
+            counts = _flat(cs, np.int64)
         use_initial = initial_list is not None and any(i is not None for i in initial_list)
-        seed0 = self._seed()
-        default_na = None if n_alleles_list is not None else np.ascontiguousarray(self.n_alleles, dtype=np.int8)
-        rs, cs, ns, ins = [], [], [], []
-        Us, Ns, As = [0] * n, [0] * n, [0] * n          # per-item scalars, assigned column-wise below
-        init_off, init_nhet = [-1] * n, [0] * n
-        io = 0
-        for i in range(n):
-            r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
-            assert r.ndim == 3
-            U, N, A = r.shape
-            na = default_na if default_na is not None else np.ascontiguousarray(n_alleles_list[i], dtype=np.int8)
-            assert len(na) == N
-            Us[i], Ns[i], As[i] = U, N, A
-            if use_initial and initial_list[i] is not None:
-                ini = np.ascontiguousarray(initial_list[i], dtype=np.int8)
-                assert ini.ndim == 3 and ini.shape[0] == self.chains and ini.shape[1] == self.ploidy
+        init_off = np.full(n, -1, dtype=np.int64)
+        init_nhet = np.zeros(n, dtype=np.int64)
+        initial = None
+        if use_initial:
+            ins, io = [], 0
+            for i, v in enumerate(initial_list):
+                if v is None:
+                    continue
+                ini = np.ascontiguousarray(v, dtype=np.int8)
+                assert ini.ndim == 3 and ini.shape[0] == self.chains and ini.shape[1] == ploidy[i]
                 init_off[i], init_nhet[i] = io, ini.shape[2]
-                ins.append(ini.ravel())
+                ins.append(ini)
                 io += ini.size
-            rs.append(r.reshape(-1))
-            ns.append(na)
-            if use_counts:
-                c = counts_list[i]
-                c = np.ones(U, dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64)
-                assert len(c) == U or U == 0
-                cs.append(c[:U])
-        U_, N_, A_ = (np.asarray(x, dtype=np.int64) for x in (Us, Ns, As))
-        excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
-        g_sizes = self.chains * self.steps * self.ploidy * N_
+            initial = _flat(ins, np.int8)
+        g_sizes = self.chains * self.steps * ploidy * N_
         l_sizes = np.full(n, self.chains * self.steps, dtype=np.int64)
         items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
-        items["reads_off"] = excl(U_ * N_ * A_)
-        items["counts_off"] = excl(U_) if use_counts else 0
-        items["nalleles_off"] = excl(N_)
-        items["genotypes_off"], items["llks_off"] = excl(g_sizes), excl(l_sizes)
-        items["n_reads"], items["n_pos"], items["max_allele"], items["ploidy"] = U_, N_, np.maximum(A_, 1), self.ploidy
-        items["temps_off"], items["n_temps"] = 0, len(temps)
-        items["seed"] = seed0 if seeds is None else (np.asarray(seeds, dtype=np.uint64) & 0xFFFFFFFF).astype(np.uint32)
-        items["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
+        items["reads_off"] = _excl(U_ * N_ * A_)
+        items["counts_off"] = _excl(U_) if use_counts else 0
+        items["nalleles_off"] = _excl(N_)
+        items["genotypes_off"], items["llks_off"] = _excl(g_sizes), _excl(l_sizes)
+        items["n_reads"], items["n_pos"], items["max_allele"], items["ploidy"] = U_, N_, np.maximum(A_, 1), ploidy
+        items["temps_off"], items["n_temps"] = t_off, t_len
+        items["seed"], items["inbreeding"] = seed, inb
         items["initial_off"], items["initial_nhet"] = init_off, init_nhet
         go, lo = int(g_sizes.sum()), int(l_sizes.sum())
-        shapes = list(zip(Ns, items["genotypes_off"].tolist(), items["llks_off"].tolist()))
-        nmax = max(Ns + [1])
-        reads = np.concatenate(rs) if rs else np.zeros(0)
-        nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
-        counts = np.concatenate(cs) if use_counts and cs else None
-        initial = np.concatenate(ins) if ins else None
-        return dict(items=items, shapes=shapes, reads=reads, counts=counts, n_alleles=nall, initial=initial,
-                    nmax=nmax, genotypes_len=go, llks_len=lo,
+        reads = _flat(arrs, np.float64)
+        return dict(items=items, reads=reads, counts=counts, n_alleles=nall, initial=initial,
+                    nmax=max(int(N_.max()) if n else 1, 1), genotypes_len=go, llks_len=lo, temperatures=pool,
                     lens=(reads.size, 0 if counts is None else counts.size, nall.size,
                           0 if initial is None else initial.size))
 
-    def _params(self, nmax, replay_words=None):
+    def _params(self, nmax, replay_words=None, temperatures=None):
         table, lens = break_table(nmax, self.alpha, self.beta, self.n_intervals)
         return make_assemble_params(
             self.steps, self.chains, self.fix_homozygous, self.recombination_step_probability,
-            self.partial_dosage_step_probability, self.dosage_step_probability, table, lens, self._temperatures(),
-            replay_words=replay_words)
+            self.partial_dosage_step_probability, self.dosage_step_probability, table, lens,
+            self._temperatures() if temperatures is None else temperatures, replay_words=replay_words)
 
+    # ------------------------------------------------------------------ full traces
     def fit_batch(self, reads_list, counts_list=None, initial_list=None, n_alleles_list=None,
-                  seeds=None, return_results=False, raw=False, replay_words=None):
+                  seeds=None, return_results=False, raw=False, replay_words=None, ploidy_list=None,
+                  inbreeding_list=None, temperatures_list=None, errors="raise"):
         """Run ``fit`` for many items in one device call.
 
-        n_alleles_list: per item allele counts (default: self.n_alleles for every item);
-        seeds: per item seeds (default: self.random_seed for every item, like the CLIs);
-        raw=True returns unsorted (genotypes, llks) arrays instead of GenotypeMultiTrace."""
+        raw=True returns unsorted (genotypes, llks) arrays instead of GenotypeMultiTrace;
+        the other keywords are described in the module docstring."""
+        assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(reads_list)
-        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds)
-        items, shapes, go, lo = pk["items"], pk["shapes"], pk["genotypes_len"], pk["llks_len"]
+        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds, ploidy_list, inbreeding_list,
+                        temperatures_list)
+        items, go, lo = pk["items"], pk["genotypes_len"], pk["llks_len"]
         out_g = np.zeros(max(go, 1), dtype=np.int8)
         out_l = np.full(max(lo, 1), np.nan, dtype=np.float64)
-        params, keep = self._params(pk["nmax"], replay_words)
+        params, keep = self._params(pk["nmax"], replay_words, pk["temperatures"])
         results = dev.assemble_call(
             items, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"], out_g, out_l,
             pk["lens"] + (go, lo))
-        out = []
-        for i, (N, g0, l0) in enumerate(shapes):
-            raise_item_status(int(results["status"][i]), i if n > 1 else None)
-            g = out_g[g0: g0 + self.chains * self.steps * self.ploidy * N].reshape(
-                self.chains, self.steps, self.ploidy, N)
-            l = out_l[l0: l0 + self.chains * self.steps].reshape(self.chains, self.steps)
+        out = [None] * n
+        cs = self.chains * self.steps
+        for i in range(n):
+            if not _settle(out, i, results["status"][i], n, errors):
+                continue
+            N, P = int(items["n_pos"][i]), int(items["ploidy"][i])
+            g0, l0 = int(items["genotypes_off"][i]), int(items["llks_off"][i])
+            g = out_g[g0: g0 + cs * P * N].reshape(self.chains, self.steps, P, N)
+            l = out_l[l0: l0 + cs].reshape(self.chains, self.steps)
             if N == 0:
                 l[:] = np.nan  # no variable position: nothing was sampled (mcmc.py:188-199)
-            out.append((g, l) if raw else GenotypeMultiTrace(g, l))
+            out[i] = (g, l) if raw else GenotypeMultiTrace(g, l)
         if return_results:
             return out, results
         return out
 
-    def _tally_helpers(self, items, burn, n, out):
+    # ------------------------------------------------------------------ tallies
+    def _tally_plan(self, items, burn, out, errors):
         """Closures shared by the fit_posterior_* methods: tally descriptors / output arrays for a set of
         items, and the unpacking of the device tallies into TraceTally objects (returns the overflowed)."""
+        n = len(items)
+
         def tally_items(idx, table):
             t = np.zeros(len(idx), dtype=TALLY_ITEM_DTYPE)
             pn = items["ploidy"][idx].astype(np.int64) * items["n_pos"][idx].astype(np.int64)
             t["genotypes_off"] = items["genotypes_off"][idx]
             t["n_pos"], t["ploidy"] = items["n_pos"][idx], items["ploidy"][idx]
             t["chains"], t["steps"], t["burn"], t["max_unique"] = self.chains, self.steps, burn, table
-            t["states_off"] = np.concatenate([[0], np.cumsum(pn * table)[:-1]])
+            t["states_off"] = _excl(pn * table)
             t["tallies_off"] = np.arange(len(idx), dtype=np.int64) * table * self.chains
             return (t, np.zeros(max(int((pn * table).sum()), 1), dtype=np.int8),
                     np.zeros(max(len(idx) * table * self.chains, 1), dtype=np.int32),
@@ -203,10 +300,13 @@ class DenovoMCMC(object):
         def collect(idx, t, tres, states, counts, first):
             over = []
             for k, i in enumerate(idx):
+                if isinstance(out[i], BaseException):
+                    continue
                 if int(tres["status"][k]) == TALLY_OVERFLOW:
                     over.append(i)
                     continue
-                raise_item_status(int(tres["status"][k]), i if n > 1 else None)
+                if not _settle(out, i, tres["status"][k], n, errors):
+                    continue
                 u = int(tres["n_het"][k])
                 P, N = int(items["ploidy"][i]), int(items["n_pos"][i])
                 so, to = int(t["states_off"][k]), int(t["tallies_off"][k])
@@ -218,8 +318,19 @@ class DenovoMCMC(object):
 
         return tally_items, collect
 
+    def _second_look(self, dev, over, kept, tally_items, collect):
+        """Items with more distinct genotypes than the first table: tally the trace that is still on
+        the device again with a table that cannot overflow."""
+        if over and kept <= 8192:
+            idx = np.array(over)
+            t, states, counts, first = tally_items(idx, kept)
+            tres = dev.trace_tally_call(t, None, 0, states, counts, first, mem_in=L.MEM_LAST_TRACE)
+            over = collect(idx, t, tres, states, counts, first)
+        return over
+
     def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None,
-                            n_alleles_list=None, seeds=None, max_unique=128):
+                            n_alleles_list=None, seeds=None, max_unique=128, ploidy_list=None,
+                            inbreeding_list=None, temperatures_list=None, errors="raise"):
         """``fit(...).burn(burn)`` for many items with the traces kept on the device: returns one
         TraceTally per item (``.posterior()``, ``.split()``, ``.replicate_incongruence()`` behave
         like the burnt GenotypeMultiTrace of the reference, mchap/application/assemble.py:123-170).
@@ -227,17 +338,17 @@ class DenovoMCMC(object):
         Only the tallies (distinct genotypes, counts and first occurrences per chain) cross the
         bus.  Items with more than ``max_unique`` distinct genotypes are tallied a second time from
         the trace still held on the device, with a table as large as the trace."""
+        assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(reads_list)
         burn = int(burn)
-        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds)
+        pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds, ploidy_list, inbreeding_list,
+                        temperatures_list)
         items = pk["items"]
-        params, keep = self._params(pk["nmax"])
+        params, keep = self._params(pk["nmax"], None, pk["temperatures"])
         kept = max(self.steps - max(burn, 0), 0) * self.chains
         out = [None] * n
-
-        tally_items, collect = self._tally_helpers(items, burn, n, out)
-
+        tally_items, collect = self._tally_plan(items, burn, out, errors)
         everything = np.arange(n)
         table = max(1, min(int(max_unique), max(kept, 1)))
         t, states, counts, first = tally_items(everything, table)
@@ -245,24 +356,22 @@ class DenovoMCMC(object):
             items, t, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"],
             pk["lens"] + (pk["genotypes_len"], pk["llks_len"]), states, counts, first)
         for i in range(n):
-            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+            _settle(out, i, results["status"][i], n, errors)
         over = collect(everything, t, tres, states, counts, first)
-        if over and kept <= 8192:
-            # second look at the same device-resident trace with a table that cannot overflow
-            idx = np.array(over)
-            t, states, counts, first = tally_items(idx, kept)
-            tres = dev.trace_tally_call(t, None, 0, states, counts, first, mem_in=L.MEM_LAST_TRACE)
-            over = collect(idx, t, tres, states, counts, first)
+        over = self._second_look(dev, over, kept, tally_items, collect)
         if over:
             # more distinct genotypes than the device table can hold: bring those traces to the host
             traces = self.fit_batch(sub2(reads_list, over), sub2(counts_list, over), sub2(initial_list, over),
-                                    sub2(n_alleles_list, over), sub2(seeds, over))
+                                    sub2(n_alleles_list, over), sub2(seeds, over), ploidy_list=sub2(ploidy_list, over),
+                                    inbreeding_list=sub2(inbreeding_list, over),
+                                    temperatures_list=sub2(temperatures_list, over))
             for i, tr in zip(over, traces):
                 out[i] = TraceTally.from_trace(tr.burn(burn))
         return out
 
     def fit_posterior_from_calls_batch(self, calls_list, probs_list, burn=0, n_alleles_list=None, seeds=None,
-                                       max_unique=128, error_factor=3):
+                                       max_unique=128, error_factor=3, ploidy_list=None, inbreeding_list=None,
+                                       temperatures_list=None, errors="raise"):
         """The whole per-sample device path in one call: integer allele calls + P(call correct)
         (mchap/application/baseclass.py:194-209 encodes and de-duplicates them on the host) ->
         de novo assembly -> tallies of the burnt trace.  Equivalent to
@@ -270,49 +379,46 @@ class DenovoMCMC(object):
         traces never leave the device.  Returns (tallies, n_unique_reads)."""
         from ..encoding import ENCODE_ITEM_DTYPE, encode_unique_reads_batch
 
+        assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(calls_list)
         burn = int(burn)
-        temps = self._temperatures()
-        cs, ps, ns = [], [], []
-        Rs, Ns, As = [0] * n, [0] * n, [0] * n
-        default_na = None if n_alleles_list is not None else np.ascontiguousarray(self.n_alleles, dtype=np.int8)
-        for i in range(n):
-            c = np.ascontiguousarray(calls_list[i], dtype=np.int8)
-            assert c.ndim == 2
-            R, N = c.shape
-            p = np.ascontiguousarray(np.broadcast_to(np.asarray(probs_list[i], dtype=np.float64), (R, N)))
-            na = default_na if default_na is not None else np.ascontiguousarray(n_alleles_list[i], dtype=np.int8)
-            assert len(na) == N
-            Rs[i], Ns[i], As[i] = R, N, (int(na.max()) if N > 0 else 0)
-            cs.append(c.reshape(-1))
-            ps.append(p.reshape(-1))
-            ns.append(na)
-        R_, N_, A_ = (np.asarray(x, dtype=np.int64) for x in (Rs, Ns, As))
-        excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        ploidy, inb, pool, t_off, t_len, seed = self._item_params(n, seeds, ploidy_list, inbreeding_list,
+                                                                  temperatures_list)
+        cs = [np.ascontiguousarray(c, dtype=np.int8) for c in calls_list]
+        assert all(c.ndim == 2 for c in cs), "calls must be [n_reads, n_positions] per item"
+        shp = np.array([c.shape for c in cs], dtype=np.int64).reshape(n, 2)
+        R_, N_ = shp[:, 0], shp[:, 1]
+        ps = [np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=np.float64), c.shape))
+              for p, c in zip(probs_list, cs)]
+        if n_alleles_list is None:
+            default_na = np.ascontiguousarray(self.n_alleles, dtype=np.int8)
+            assert n == 0 or (N_ == len(default_na)).all()
+            nas = [default_na] * n
+        else:
+            nas = [np.asarray(a, dtype=np.int8) for a in n_alleles_list]
+            assert [len(a) for a in nas] == N_.tolist()
+        A_ = np.array([int(a.max()) if len(a) else 0 for a in nas], dtype=np.int64)
         enc = np.zeros(n, dtype=ENCODE_ITEM_DTYPE)
-        enc["calls_off"] = enc["probs_off"] = excl(R_ * N_)
-        enc["nalleles_off"] = excl(N_)
-        enc["reads_off"], enc["counts_off"] = excl(R_ * N_ * A_), excl(R_)
+        enc["calls_off"] = enc["probs_off"] = _excl(R_ * N_)
+        enc["nalleles_off"] = _excl(N_)
+        enc["reads_off"], enc["counts_off"] = _excl(R_ * N_ * A_), _excl(R_)
         enc["n_reads"], enc["n_pos"], enc["max_allele"] = R_, N_, A_
         items = np.zeros(n, dtype=ASSEMBLE_ITEM_DTYPE)
-        g_sizes = self.chains * self.steps * self.ploidy * N_
-        items["genotypes_off"] = excl(g_sizes)
+        g_sizes = self.chains * self.steps * ploidy * N_
+        items["genotypes_off"] = _excl(g_sizes)
         items["llks_off"] = np.arange(n, dtype=np.int64) * (self.chains * self.steps)
-        items["n_pos"], items["max_allele"], items["ploidy"] = N_, np.maximum(A_, 1), self.ploidy
-        items["temps_off"], items["n_temps"] = 0, len(temps)
-        items["seed"] = self._seed() if seeds is None else (np.asarray(seeds, dtype=np.uint64) & 0xFFFFFFFF).astype(np.uint32)
-        items["inbreeding"] = np.nan if self.inbreeding is None else float(self.inbreeding)
+        items["n_pos"], items["max_allele"], items["ploidy"] = N_, np.maximum(A_, 1), ploidy
+        items["temps_off"], items["n_temps"] = t_off, t_len
+        items["seed"], items["inbreeding"] = seed, inb
         items["initial_off"] = -1
         go, lo = int(g_sizes.sum()), n * self.chains * self.steps
-        nmax = max(Ns + [1])
-        calls = np.concatenate(cs) if cs else np.zeros(0, dtype=np.int8)
-        probs = np.concatenate(ps) if ps else np.zeros(0)
-        nall = np.concatenate(ns) if ns else np.zeros(0, dtype=np.int8)
-        params, keep = self._params(nmax)
+        nmax = max(int(N_.max()) if n else 1, 1)
+        calls, probs, nall = _flat(cs, np.int8), _flat(ps, np.float64), _flat(nas, np.int8)
+        params, keep = self._params(nmax, None, pool)
         kept = max(self.steps - max(burn, 0), 0) * self.chains
         out = [None] * n
-        tally_items, collect = self._tally_helpers(items, burn, n, out)
+        tally_items, collect = self._tally_plan(items, burn, out, errors)
         everything = np.arange(n)
         table = max(1, min(int(max_unique), max(kept, 1)))
         t, states, counts, first = tally_items(everything, table)
@@ -325,20 +431,17 @@ class DenovoMCMC(object):
             _ptr(first), counts.size, _ptr(eres), _ptr(results), _ptr(tres))
         dev._check(rc)
         for i in range(n):
-            raise_item_status(int(eres["status"][i]), i if n > 1 else None)
-            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+            if _settle(out, i, eres["status"][i], n, errors):
+                _settle(out, i, results["status"][i], n, errors)
         over = collect(everything, t, tres, states, counts, first)
-        if over and kept <= 8192:
-            idx = np.array(over)
-            t, states, counts, first = tally_items(idx, kept)
-            tres = dev.trace_tally_call(t, None, 0, states, counts, first, mem_in=L.MEM_LAST_TRACE)
-            over = collect(idx, t, tres, states, counts, first)
+        over = self._second_look(dev, over, kept, tally_items, collect)
         if over:
-            pairs = encode_unique_reads_batch(sub2(calls_list, over), sub2(probs_list, over),
-                                              [self.n_alleles] * len(over) if n_alleles_list is None
-                                              else sub2(n_alleles_list, over), error_factor, dev)
-            traces = self.fit_batch([r for r, _ in pairs], [c for _, c in pairs], None, sub2(n_alleles_list, over),
-                                    sub2(seeds, over))
+            pairs = encode_unique_reads_batch(sub2(calls_list, over), sub2(probs_list, over), [nas[i] for i in over],
+                                              error_factor, dev)
+            traces = self.fit_batch([r for r, _ in pairs], [c for _, c in pairs], None, [nas[i] for i in over],
+                                    seed[over], ploidy_list=ploidy[over], inbreeding_list=[
+                                        None if np.isnan(inb[i]) else inb[i] for i in over],
+                                    temperatures_list=sub2(temperatures_list, over))
             for i, tr in zip(over, traces):
                 out[i] = TraceTally.from_trace(tr.burn(burn))
         return out, eres["n_het"].astype(np.int64)

@@ -8,7 +8,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .. import _lib as L
-from ..api import TALLY_ITEM_DTYPE, CallBatch, count_genotypes, default_device, raise_item_status
+from ..api import TALLY_ITEM_DTYPE, CallBatch, count_genotypes, default_device, item_status_error
 from ..assemble.classes import unique_first_occurrence
 
 __all__ = ["CallingMCMC", "GenotypeAllelesMultiTrace", "PosteriorGenotypeAllelesDistribution", "AllelesTraceTally"]
@@ -39,12 +39,14 @@ class PosteriorGenotypeAllelesDistribution(object):
 
     def as_array(self, n_alleles):
         """Dense VCF-order probability vector (calling/utils.py:60-86)."""
-        from ..jitutils import genotypes_as_indices
+        from ..jitutils import genotype_alleles_as_index
 
         _, ploidy = self.genotypes.shape
         out = np.zeros(count_genotypes(n_alleles, ploidy), dtype=np.float64)
-        if len(self.genotypes):
-            out[genotypes_as_indices(self.genotypes)] = self.probabilities
+        # a handful of distinct genotypes per trace: host integers (the array form of the ranking
+        # runs on the device, jitutils.genotypes_as_indices)
+        for gen, p in zip(self.genotypes, self.probabilities):
+            out[genotype_alleles_as_index(gen)] = p
         return out
 
     def allele_frequencies(self, dosage=False):
@@ -211,92 +213,114 @@ class CallingMCMC(object):
             return GenotypeAllelesMultiTrace(genotypes, llks, len(self.haplotypes))
         return self.fit_batch([reads], [read_counts], None if initial is None else [initial])[0]
 
-    def fit_batch(self, reads_list, counts_list=None, initial_list=None, haplotypes_list=None, priors=None,
-                  seeds=None, return_results=False, replay_words=None):
-        """``fit`` for many items in one device call.  haplotypes_list / priors default to the
-        model's haplotypes / prior for every item; seeds default to random_seed like the CLI."""
-        dev = self.device or default_device()
+    def _prepare(self, reads_list, counts_list, initial_list, haplotypes_list, priors, seeds, ploidy_list):
+        """CallBatch + output offsets, seeds and initial genotypes of a batch."""
         n = len(reads_list)
-        st = self._step_type()
         haps = [self.haplotypes] * n if haplotypes_list is None else haplotypes_list
         prs = ([self.prior] * n if self.prior is not None else None) if priors is None else priors
-        batch = CallBatch(reads_list, haps, self.ploidy, counts_list, prs)
+        ploidy = (np.full(n, int(self.ploidy), dtype=np.int64) if ploidy_list is None
+                  else np.asarray(ploidy_list, dtype=np.int64).reshape(n))
+        batch = CallBatch(reads_list, haps, ploidy, counts_list, prs)
         seed0 = int(self.random_seed) & 0xFFFFFFFF if self.random_seed is not None else int(
             np.random.randint(0, 2 ** 32, dtype=np.uint64))
         items = batch.items
-        P = self.ploidy
         per = self.chains * self.steps
-        idx = np.arange(n, dtype=np.int64)
-        items["gl_off"] = idx * per * P
-        items["hap_out_off"] = idx * per
+        a_off = np.zeros(n, dtype=np.int64)
+        if n > 1:
+            np.cumsum(per * ploidy[:-1], out=a_off[1:])
+        items["gl_off"] = a_off
+        items["hap_out_off"] = np.arange(n, dtype=np.int64) * per
         sd = np.full(n, seed0, dtype=np.uint32) if seeds is None else np.asarray(seeds, dtype=np.uint64).astype(np.uint32)
         items["reserved"] = sd.view(np.int32)
+        pmax = int(ploidy.max()) if n else 1
         init = None
         if initial_list is not None and any(i is not None for i in initial_list):
-            init = np.full((n, P), -1, dtype=np.int32)
+            init = np.full((n, pmax), -1, dtype=np.int32)
             for i, v in enumerate(initial_list):
                 if v is not None:
-                    init[i] = np.asarray(v, dtype=np.int32)
-        out = dev.call_mcmc(batch, self.steps, self.chains, st, init, P, replay_words)
-        res = []
+                    init[i, :ploidy[i]] = np.asarray(v, dtype=np.int32)
+        return batch, haps, prs, ploidy, pmax, init
+
+    def fit_batch(self, reads_list, counts_list=None, initial_list=None, haplotypes_list=None, priors=None,
+                  seeds=None, return_results=False, replay_words=None, ploidy_list=None, errors="raise"):
+        """``fit`` for many items in one device call.  haplotypes_list / priors / ploidy_list default
+        to the model's haplotypes / prior / ploidy for every item; seeds default to random_seed like
+        the CLI; errors="return" stores a failing item's exception in its slot instead of raising."""
+        assert errors in ("raise", "return")
+        dev = self.device or default_device()
+        n = len(reads_list)
+        batch, haps, prs, ploidy, pmax, init = self._prepare(reads_list, counts_list, initial_list, haplotypes_list,
+                                                             priors, seeds, ploidy_list)
+        out = dev.call_mcmc(batch, self.steps, self.chains, self._step_type(), init, pmax, replay_words)
+        per = self.chains * self.steps
+        res = [None] * n
         for i in range(n):
-            raise_item_status(int(out["results"]["status"][i]), i if n > 1 else None)
-            g = out["alleles"][i * per * P:(i + 1) * per * P].reshape(self.chains, self.steps, P)
+            exc = item_status_error(int(out["results"]["status"][i]), i if n > 1 else None)
+            if exc is not None:
+                if errors == "raise":
+                    raise exc
+                res[i] = exc
+                continue
+            P, a0 = int(ploidy[i]), int(batch.items["gl_off"][i])
+            g = out["alleles"][a0:a0 + per * P].reshape(self.chains, self.steps, P)
             l = out["llks"][i * per:(i + 1) * per].reshape(self.chains, self.steps)
-            res.append(GenotypeAllelesMultiTrace(g, l, len(haps[i])))
+            res[i] = GenotypeAllelesMultiTrace(g, l, len(haps[i]))
         if return_results:
             return res, out["results"]
         return res
 
     def fit_posterior_batch(self, reads_list, counts_list=None, burn=0, initial_list=None, haplotypes_list=None,
-                            priors=None, seeds=None, max_unique=128):
+                            priors=None, seeds=None, max_unique=128, ploidy_list=None, errors="raise"):
         """``fit(...).burn(burn)`` for many items with the traces kept on the device: one
         AllelesTraceTally per item (mchap/application/call.py:134-182 consumes exactly its methods)."""
+        assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(reads_list)
         st = self._step_type()
         burn = int(burn)
-        haps = [self.haplotypes] * n if haplotypes_list is None else haplotypes_list
-        prs = ([self.prior] * n if self.prior is not None else None) if priors is None else priors
-        batch = CallBatch(reads_list, haps, self.ploidy, counts_list, prs)
-        seed0 = int(self.random_seed) & 0xFFFFFFFF if self.random_seed is not None else int(
-            np.random.randint(0, 2 ** 32, dtype=np.uint64))
+        batch, haps, prs, ploidy, pmax, init = self._prepare(reads_list, counts_list, initial_list, haplotypes_list,
+                                                             priors, seeds, ploidy_list)
         items = batch.items
-        P = self.ploidy
-        per = self.chains * self.steps
         idx = np.arange(n, dtype=np.int64)
-        items["gl_off"] = idx * per * P
-        items["hap_out_off"] = idx * per
-        sd = np.full(n, seed0, dtype=np.uint32) if seeds is None else np.asarray(seeds, dtype=np.uint64).astype(np.uint32)
-        items["reserved"] = sd.view(np.int32)
-        init = None
-        if initial_list is not None and any(i is not None for i in initial_list):
-            init = np.full((n, P), -1, dtype=np.int32)
-            for i, v in enumerate(initial_list):
-                if v is not None:
-                    init[i] = np.asarray(v, dtype=np.int32)
         kept = max(self.steps - max(burn, 0), 0) * self.chains
         out = [None] * n
 
+        def settle(i, status):
+            exc = item_status_error(int(status), i if n > 1 else None)
+            if exc is None:
+                return True
+            if errors == "raise":
+                raise exc
+            out[i] = exc
+            return False
+
         def tally_items(sel, table):
             t = np.zeros(len(sel), dtype=TALLY_ITEM_DTYPE)
+            P_ = ploidy[sel]
             t["genotypes_off"] = items["gl_off"][sel]
-            t["n_pos"], t["ploidy"] = 1, P
+            t["n_pos"], t["ploidy"] = 1, P_
             t["chains"], t["steps"], t["burn"], t["max_unique"] = self.chains, self.steps, burn, table
-            t["states_off"] = np.arange(len(sel), dtype=np.int64) * table * P
+            so = np.zeros(len(sel), dtype=np.int64)
+            if len(sel) > 1:
+                np.cumsum(table * P_[:-1], out=so[1:])
+            t["states_off"] = so
             t["tallies_off"] = np.arange(len(sel), dtype=np.int64) * table * self.chains
-            return (t, np.zeros(max(len(sel) * table * P, 1), dtype=np.int32),
+            return (t, np.zeros(max(int((table * P_).sum()), 1), dtype=np.int32),
                     np.zeros(max(len(sel) * table * self.chains, 1), dtype=np.int32),
                     np.zeros(max(len(sel) * table * self.chains, 1), dtype=np.int32))
 
         def collect(sel, t, tres, states, counts, first):
             over = []
             for k, i in enumerate(sel):
+                if isinstance(out[i], BaseException):
+                    continue
                 if int(tres["status"][k]) == L.ITEM_TALLY_OVERFLOW:
                     over.append(i)
                     continue
-                raise_item_status(int(tres["status"][k]), i if n > 1 else None)
+                if not settle(i, tres["status"][k]):
+                    continue
                 u = int(tres["n_het"][k])
+                P = int(ploidy[i])
                 so, to = int(t["states_off"][k]), int(t["tallies_off"][k])
                 out[i] = AllelesTraceTally(
                     states[so: so + u * P].reshape(u, P).copy(),
@@ -306,9 +330,9 @@ class CallingMCMC(object):
 
         table = max(1, min(int(max_unique), max(kept, 1)))
         t, states, counts, first = tally_items(idx, table)
-        results, tres = dev.call_mcmc_tally(batch, t, self.steps, self.chains, st, states, counts, first, init, P)
+        results, tres = dev.call_mcmc_tally(batch, t, self.steps, self.chains, st, states, counts, first, init, pmax)
         for i in range(n):
-            raise_item_status(int(results["status"][i]), i if n > 1 else None)
+            settle(i, results["status"][i])
         over = collect(idx, t, tres, states, counts, first)
         if over and kept <= 8192:
             sel = np.array(over)
@@ -318,7 +342,7 @@ class CallingMCMC(object):
         if over:
             pick = lambda lst: None if lst is None else [lst[i] for i in over]
             traces = self.fit_batch(pick(reads_list), pick(counts_list), pick(initial_list), [haps[i] for i in over],
-                                    pick(prs), pick(seeds))
+                                    pick(prs), pick(seeds), ploidy_list=ploidy[over])
             for i, tr in zip(over, traces):
                 out[i] = AllelesTraceTally.from_trace(tr.burn(burn))
         return out

@@ -77,6 +77,50 @@ def _posterior_items(n_genotypes, ploidy, n_alleles, prior):
     return items, freqs
 
 
+def genotype_posteriors_batch(llks_list, ploidy, n_alleles_list, priors=None, device=None, with_frequencies=False):
+    """genotype_posteriors for many items in one device call (``ploidy`` scalar or per item):
+    list of f64[G] arrays; with_frequencies=True also returns the per-item (frequencies, counts,
+    occurrence) triples of posterior_allele_frequencies computed by the same kernel."""
+    dev = device or default_device()
+    n = len(llks_list)
+    ploidies = np.broadcast_to(np.asarray(ploidy, dtype=np.int64), (n,))
+    ls = [np.ascontiguousarray(l) for l in llks_list]
+    is32 = n > 0 and all(l.dtype == np.float32 for l in ls)
+    if not is32:
+        ls = [np.ascontiguousarray(l, dtype=np.float64) for l in ls]
+    G_ = np.array([len(l) for l in ls], dtype=np.int64)
+    H_ = np.asarray(n_alleles_list, dtype=np.int64).reshape(n)
+    for g, h, p in zip(G_, H_, ploidies):
+        assert count_genotypes(int(h), int(p)) == g
+    items = np.zeros(n, dtype=CALL_ITEM_DTYPE)
+    excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+    items["ploidy"], items["n_haps"] = ploidies, H_
+    items["gl_off"], items["hap_out_off"] = excl(G_), excl(H_)
+    items["freqs_off"], items["inbreeding"] = -1, np.nan
+    fs, fo = [], 0
+    for i in range(n):
+        prior = None if priors is None else priors[i]
+        if prior is not None:
+            items["inbreeding"][i] = float(prior[0])
+            if prior[1] is not None:
+                fr = np.ascontiguousarray(prior[1], dtype=np.float64)
+                assert len(fr) == H_[i]
+                items["freqs_off"][i] = fo
+                fs.append(fr)
+                fo += len(fr)
+    freqs = np.concatenate(fs) if fs else None
+    llks = np.concatenate(ls) if n else np.zeros(0)
+    gp, of, oc, oo = dev.genotype_posteriors(items, llks, freqs, int(G_.sum()), int(H_.sum()),
+                                             with_frequencies=with_frequencies)
+    goff, hoff = items["gl_off"], items["hap_out_off"]
+    out = [gp[int(o): int(o) + int(g)] for o, g in zip(goff, G_)]
+    if not with_frequencies:
+        return out
+    trip = [(of[int(o): int(o) + int(h)], oc[int(o): int(o) + int(h)], oo[int(o): int(o) + int(h)])
+            for o, h in zip(hoff, H_)]
+    return out, trip
+
+
 def genotype_posteriors(log_likelihoods, ploidy, n_alleles, prior=None, device=None):
     """Posterior probability of every genotype in VCF order; a float32 input is handled with the
     reference's mixed precision (sum rounded to float32, normalisation in float64)."""

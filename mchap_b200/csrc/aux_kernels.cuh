@@ -143,6 +143,52 @@ __global__ void unrank_kernel(const int64_t *index, int64_t n, int ploidy, int64
 }
 
 // ---------------------------------------------------------------------------------------
+// encoding/integer/stats.py:18-39 minimum_error_correction for a batch of (read calls, genotype)
+// pairs, one warp per pair: lane = read; per read the number of called positions (call >= 0) that
+// differ from a haplotype, minimised over the haplotypes.  Byte/integer work: reads the int8 calls
+// once (coalesced along the read row), the genotype through the read-only path.
+// Outputs per item: sum over reads (what the CLIs report as MEC), number of calls >= 0 (the MECP
+// denominator, application/assemble.py:160-163) and optionally the per-read values.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mec_batch_kernel(const mchb_mec_item *items, int64_t n_items,
+                                                        const int8_t *calls, const int8_t *genotypes,
+                                                        int64_t *out_mec, int64_t *out_called, int32_t *out_per_read) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_items) return;
+    const mchb_mec_item it = items[w];
+    const int R = it.n_reads, N = it.n_pos, P = it.ploidy;
+    const int8_t *C = calls + it.calls_off;
+    const int8_t *G = genotypes + it.geno_off;
+    long long total = 0, called = 0;
+    for (int r = lane; r < R; r += 32) {
+        const int8_t *row = C + (size_t)r * N;
+        int best = 0x7fffffff, ncall = 0;
+        for (int j = 0; j < N; j++) ncall += row[j] >= 0;
+        for (int h = 0; h < P; h++) {
+            int d = 0;
+            for (int j = 0; j < N; j++) {
+                const int c = row[j];
+                d += (c >= 0) && (c != (int)__ldg(G + h * N + j));
+            }
+            best = min(best, d);
+        }
+        if (P == 0) best = 0;
+        total += best;
+        called += ncall;
+        if (out_per_read) out_per_read[it.per_read_off + r] = best;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        total += __shfl_xor_sync(MCHB_FULL, total, o);
+        called += __shfl_xor_sync(MCHB_FULL, called, o);
+    }
+    if (lane == 0) {
+        out_mec[w] = total;
+        if (out_called) out_called[w] = called;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // FP64 SIMT pipe probe: 8 independent DFMA chains per thread.  Used by bench.py to measure the
 // roofline denominator of the (FP64-bound) MCMC kernels live on the device under test.
 // ---------------------------------------------------------------------------------------

@@ -1683,3 +1683,53 @@ extern "C" int mchb_encode_assemble_tally_batch(mchb_handle *h, const mchb_assem
     h->launches += total_launches;
     return rc;
 }
+
+// --------------------------------------------------------------- minimum error correction
+extern "C" int mchb_mec_batch(mchb_handle *h, int mem, const mchb_mec_item *items, int64_t n_items,
+                              const int8_t *calls, int64_t calls_len, const int8_t *genotypes,
+                              int64_t genotypes_len, int64_t *out_mec, int64_t *out_called,
+                              int32_t *out_per_read, int64_t per_read_len) {
+    if (!h || !items || !out_mec || n_items < 0) return MCHB_ERR_ARGUMENT;
+    begin_call(h);
+    CK(cudaSetDevice(h->device));
+    if (n_items == 0) return MCHB_OK;
+    for (int64_t i = 0; i < n_items; i++) {
+        const mchb_mec_item &it = items[i];
+        const int64_t rn = (int64_t)it.n_reads * it.n_pos;
+        bool bad = it.n_reads < 0 || it.n_pos < 0 || it.ploidy < 0 || it.calls_off < 0 || it.calls_off + rn > calls_len ||
+                   it.geno_off < 0 || it.geno_off + (int64_t)it.ploidy * it.n_pos > genotypes_len ||
+                   (out_per_read && (it.per_read_off < 0 || it.per_read_off + it.n_reads > per_read_len));
+        if (bad) {
+            h->err = "mec item " + std::to_string(i) + " exceeds the given array lengths";
+            return MCHB_ERR_ARGUMENT;
+        }
+    }
+    int rc;
+    void *ditems;
+    if ((rc = ensure(h, S_ITEMS, sizeof(mchb_mec_item) * (size_t)n_items, &ditems))) return rc;
+    CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_mec_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
+    const int8_t *dcalls, *dgeno;
+    int64_t *dmec, *dcalled = nullptr;
+    int32_t *dper = nullptr;
+    if ((rc = stage_in(h, mem, S_ECALLS, calls, calls_len, &dcalls))) return rc;
+    if ((rc = stage_in(h, mem, S_GENO, genotypes, genotypes_len, &dgeno))) return rc;
+    if ((rc = stage_out(h, mem, S_AUX0, out_mec, n_items, &dmec))) return rc;
+    if (out_called && (rc = stage_out(h, mem, S_AUX1, out_called, n_items, &dcalled))) return rc;
+    if (out_per_read && (rc = stage_out(h, mem, S_OUT_A32, out_per_read, per_read_len, &dper))) return rc;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    mec_batch_kernel<<<(unsigned)((n_items + 3) / 4), 128, 0, h->stream>>>((const mchb_mec_item *)ditems, n_items, dcalls,
+                                                                            dgeno, dmec, dcalled, dper);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->launches++;
+    if (mem == MCHB_MEM_HOST) {
+        CK(cudaMemcpyAsync(out_mec, dmec, sizeof(int64_t) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+        if (out_called)
+            CK(cudaMemcpyAsync(out_called, dcalled, sizeof(int64_t) * (size_t)n_items, cudaMemcpyDeviceToHost, h->stream));
+        if (out_per_read && per_read_len > 0)
+            CK(cudaMemcpyAsync(out_per_read, dper, sizeof(int32_t) * (size_t)per_read_len, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->kernel_ms, h->ev0, h->ev1));
+    return MCHB_OK;
+}
