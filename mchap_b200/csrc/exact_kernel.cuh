@@ -6,15 +6,28 @@
 //   295-329 genotype_posteriors, 332-369 posterior_allele_frequencies;
 //   calling/prior.py:116-179; jitutils.py:113-146 (increment), 253-318 (rank / unrank).
 //
-// Design: one CTA per (locus, sample) item.
-//   1. the read x haplotype table t[r][h] = (prod_j reads[r,j,hap[h,j]], gaps skipped) / ploidy is
-//      built once in shared memory (a gather-product over positions: not a GEMM, stays SIMT);
-//   2. the G = C(H+P-1, P) genotypes are split into contiguous VCF-order chunks, one per thread:
-//      the thread unranks its first genotype and then walks with increment_genotype; the
-//      log-likelihood of a genotype sums log(sum_k t[r][g_k]) * count_r over reads IN READ ORDER,
-//      exactly the reference's operation order, so values differ only by log() ULPs;
-//   3. mode (first maximum, strict >), normaliser (log-sum-exp) and allele statistics are block
-//      reductions; log joints are parked in a per-CTA global scratch row for the second pass.
+// Design: one CTA per (locus, sample) item, one thread per contiguous VCF-order chunk of the
+// G = C(H+P-1, P) genotypes.
+//   1. the read x haplotype table t[h][r] = (prod_j reads[r,j,hap[h,j]], gaps skipped) / ploidy is
+//      built once in shared memory, haplotype-major with an odd row stride: a thread keeps one row
+//      pointer per genotype slot in registers and the inner loop is P shared loads with immediate
+//      offsets and P-1 adds per read (a gather-product / gather-sum: not a GEMM, stays SIMT);
+//   2. the per-read probability rp = sum_k t[g_k][r] keeps the reference's left fold, and the
+//      log-likelihood sum_r c_r log(rp_r) is evaluated as the log of a product: the mantissas of the
+//      rp_r are multiplied and their exponents added as integers, with ONE log per genotype instead
+//      of one per read.  That is the same real number; its rounding error (<= n_reads * 2^-53
+//      relative on the product, nothing on the exponents) is below the accumulated rounding of the
+//      reference's own sum.  Reads with a count above 16, zero / denormal / non-finite rp take the
+//      reference's form (log(rp) * count);
+//   3. a genotype moves to its VCF-order successor in registers; a thread's first genotype is
+//      unranked from a binomial table C(n+p-1, p) that the CTA keeps in shared memory;
+//   4. every reduction is in a fixed order, so results are reproducible bit for bit from run to
+//      run: per-thread partials over the contiguous chunk, combined in thread order.  The
+//      normaliser is M + log(sum_g exp(ljoint_g - M)) with M the largest log joint, and the allele
+//      statistics accumulate exp(ljoint_g - M) in per-thread shared-memory rows;
+//   5. log joints are parked in a per-CTA global scratch row between the passes when the rows of
+//      the whole grid fit the caller's budget, otherwise they are evaluated again in the second pass
+//      (the reference's own low-memory scheme, exact.py:108-153).
 #pragma once
 #include "common.cuh"
 
@@ -34,100 +47,217 @@ struct ExactArgs {
     double *out_freqs;          // per item at hap_out_off: posterior mean allele frequencies
     double *out_occur;          // per item at hap_out_off: posterior occurrence
     float *out_gl;              // per item at gl_off (mode 1)
-    double *scratch;            // [gridDim.x, scratch_stride] log joints
+    double *scratch;            // [gridDim.x, scratch_stride] log joints; null: evaluate twice
     int64_t scratch_stride;
     int32_t *work_counter;
     mchb_item_result *results;
     int32_t umax, hmax, pmax;   // shared memory geometry
+    int32_t part_threads;       // threads that own a partial row of allele statistics (power of two <= 128)
 };
 
-// up to 16 allele indices (< 256) packed in two words
-struct Geno {
-    uint64_t lo, hi;
-    __device__ __forceinline__ int get(int k) const { return (int)(((k < 8 ? lo : hi) >> (8 * (k & 7))) & 255u); }
-    __device__ __forceinline__ void set(int k, int v) {
-        uint64_t m = ~(255ull << (8 * (k & 7)));
-        uint64_t x = (uint64_t)v << (8 * (k & 7));
-        if (k < 8) lo = (lo & m) | x;
-        else hi = (hi & m) | x;
+// fdlibm's split of ln 2: E * LN2_HI is exact for |E| < 2^20
+#define MCHB_LN2_HI 6.93147180369123816490e-01
+#define MCHB_LN2_LO 1.90821492927058770002e-10
+// read counts up to this take the product form (count factors of the mantissa); larger ones log(rp) * count
+#define MCHB_EXACT_POW_MAX 16
+
+// Shared-memory carve-up of the exhaustive kernels (doubles unless noted), host mirror: exact_smem().
+struct ExactSmem {
+    double *tab;      // [hmax][us]     read x haplotype table, haplotype-major
+    double *lgA;      // [hmax]         lgamma(alpha_a)
+    double *lgDA;     // [hmax][pmax+1] lgamma(d + alpha_a)
+    double *fr;       // [hmax]         prior allele frequencies (staged)
+    double *part;     // [part_threads][hs][2] partial allele statistics
+    double *red;      // [32]: [0..7] per-warp sums, [8..] per-warp mode records / maxima
+    long long *cwr;   // [(hmax+1)][pmax+1] C(n+p-1, p)
+    int *cnt;         // [umax] read counts
+    int us, hs;
+};
+
+__device__ __forceinline__ ExactSmem exact_carve(unsigned char *raw, int umax, int hmax, int pmax, int part_threads) {
+    ExactSmem s;
+    s.us = umax | 1;
+    s.hs = hmax | 1;
+    s.tab = reinterpret_cast<double *>(raw);
+    s.lgA = s.tab + (size_t)hmax * s.us;
+    s.lgDA = s.lgA + hmax;
+    s.fr = s.lgDA + (size_t)hmax * (pmax + 1);
+    s.part = s.fr + hmax;
+    s.red = s.part + (size_t)part_threads * s.hs * 2;
+    s.cwr = reinterpret_cast<long long *>(s.red + 32);
+    s.cnt = reinterpret_cast<int *>(s.cwr + (size_t)(hmax + 1) * (pmax + 1));
+    return s;
+}
+
+// C(n+p-1, p) for n = 0..H, p = 0..P by Pascal's rule (jitutils.py:213-250 conventions:
+// cwr(n, 0) = 1 for n >= 1, cwr(0, p) = 0 including p = 0).  Values beyond int64 saturate.
+__device__ __forceinline__ void exact_fill_cwr(long long *cwr, int H, int P, int pstride, int tid, int nthr) {
+    // column p needs column p-1: P is small, so one thread per row sweeps p with a barrier per column
+    for (int p = 0; p <= P; p++) {
+        if (p == 0) {
+            for (int n = tid; n <= H; n += nthr) cwr[n * pstride] = n == 0 ? 0 : 1;
+        } else if (tid == 0) {
+            long long acc = 0;
+            cwr[p] = 0;
+            for (int n = 1; n <= H; n++) {
+                // cwr(n, p) = cwr(n-1, p) + cwr(n, p-1)
+                const long long add = cwr[n * pstride + p - 1];
+                acc = (acc > 0x7fffffffffffffffLL - add) ? 0x7fffffffffffffffLL : acc + add;
+                cwr[n * pstride + p] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Genotype of PM register slots (slots >= P unused), the row pointer of every slot and the
+// successor / unrank operations on them.
+template <int PM>
+struct GenoR {
+    int g[PM];
+
+    // jitutils.py:279-318 with the shared binomial table
+    __device__ __forceinline__ void unrank(long long index, int P, const long long *cwr, int pstride, int H) {
+        long long rem = index;
+#pragma unroll
+        for (int k = PM - 1; k >= 0; k--) {
+            if (k < P) {
+                // largest a with cwr(a, k+1) <= rem
+                int a = 0;
+                while (a < H && cwr[(a + 1) * pstride + k + 1] <= rem) a++;
+                rem -= cwr[a * pstride + k + 1];
+                g[k] = a;
+            } else {
+                g[k] = 0;
+            }
+        }
+    }
+    // jitutils.py:113-146
+    __device__ __forceinline__ void increment(int P) {
+        int i = P;  // all equal: bump the last slot
+#pragma unroll
+        for (int k = PM - 1; k >= 1; k--)
+            if (k < P && g[k] != g[k - 1]) i = k;
+#pragma unroll
+        for (int k = 0; k < PM; k++) {
+            if (k == i - 1) g[k] += 1;
+            else if (k < i - 1) g[k] = 0;
+        }
+    }
+    // jitutils.py:253-276
+    __device__ __forceinline__ long long rank(int P, const long long *cwr, int pstride) const {
+        long long index = 0;
+#pragma unroll
+        for (int k = 0; k < PM; k++)
+            if (k < P) index += cwr[g[k] * pstride + k + 1];
+        return index;
     }
 };
 
-// jitutils.py:113-146 on a sorted packed genotype
-__device__ __forceinline__ void geno_increment(Geno &g, int P) {
-    if (P == 1) {
-        g.set(0, g.get(0) + 1);
-        return;
-    }
-    int prev = g.get(0);
-    for (int i = 1; i < P; i++) {
-        int al = g.get(i);
-        if (al == prev) continue;
-        g.set(i - 1, g.get(i - 1) + 1);
-        for (int m = 0; m < i - 1; m++) g.set(m, 0);
-        return;
-    }
-    g.set(P - 1, g.get(P - 1) + 1);
-    for (int m = 0; m < P - 1; m++) g.set(m, 0);
-}
+struct ExactItem {
+    int U, P, H;
+    bool unit_counts, has_prior, null_prior, has_freqs;
+    double lg_left, p_log_h;
+};
 
-// jitutils.py:279-318
-__device__ inline Geno geno_unrank(long long index, int P) {
-    Geno g;
-    g.lo = 0;
-    g.hi = 0;
-    long long remainder = index;
-    for (int it = 0; it < P; it++) {
-        int p = P - it;
-        long long a = -1, nw = 0, prev = 0;
-        while (nw <= remainder) {
-            a += 1;
-            prev = nw;
-            nw = comb_with_replacement(a, p);
+// sum_r count_r * log(sum_k t[g_k][r]) for one genotype (header, point 2)
+template <int PM>
+__device__ __forceinline__ double exact_llk(const GenoR<PM> &g, const ExactSmem &s, const ExactItem &it) {
+    const double *row[PM];
+#pragma unroll
+    for (int k = 0; k < PM; k++) row[k] = s.tab + (size_t)g.g[k] * s.us;
+    double mant = 1.0, slow = 0.0;
+    int expo = 0, n_fast = 0, n_norm = 0;
+    bool odd = false;  // some rp is zero, denormal, negative, inf or NaN
+#pragma unroll 4
+    for (int r = 0; r < it.U; r++) {
+        double rp = row[0][r];
+#pragma unroll
+        for (int k = 1; k < PM; k++)
+            if (k < it.P) rp += row[k][r];
+        const int hi = __double2hiint(rp);
+        odd = odd || (hi < 0x00100000) || (hi >= 0x7ff00000);
+        const int c = it.unit_counts ? 1 : s.cnt[r];  // uniform over the CTA
+        if (c >= 1 && c <= MCHB_EXACT_POW_MAX) {
+            // rp^c: c factors of the mantissa, c times the exponent
+            const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(rp));
+            expo += (hi >> 20) * c;
+            n_fast += c;
+            mant *= m;
+#pragma unroll 1
+            for (int q = 1; q < c; q++) mant *= m;
+            if (n_fast - n_norm >= 512) {  // keep the mantissa product far from overflow
+                const int mh = __double2hiint(mant);
+                expo += (mh >> 20) - 1023;
+                mant = __hiloint2double((mh & 0x000fffff) | 0x3ff00000, __double2loint(mant));
+                n_norm = n_fast;
+            }
+        } else {
+            slow += log(rp) * (double)c;
         }
-        a -= 1;
-        remainder -= prev;
-        g.set(p - 1, (int)a);
     }
-    return g;
-}
-
-// jitutils.py:253-276
-__device__ inline long long geno_rank(const Geno &g, int P) {
-    long long index = 0;
-    for (int i = 0; i < P; i++) index += comb_with_replacement(g.get(i), i + 1);
-    return index;
-}
-
-// calling/prior.py:116-179 for a packed genotype.  lgA[a] = lgamma(alpha_a) and
-// lgDA[a*(P+1)+d] = lgamma(d + alpha_a) are per-item tables in shared memory (only when
-// inbreeding > 0); freqs may be null.
-__device__ __forceinline__ double exact_log_prior(const Geno &g, int P, int H, double inbreeding, const double *freqs,
-                                                  const double *lgA, const double *lgDA, double lg_left,
-                                                  double log_H) {
-    double acc = 0.0;  // ln_denom (null prior) or prod (Dirichlet-multinomial)
-    const bool null_prior = inbreeding == 0.0;
-    for (int i = 0; i < P; i++) {
-        const int ai = g.get(i);
-        int cntv = 0;
-        bool first = true;
-        for (int k = 0; k < P; k++) {
-            bool eq = g.get(k) == ai;
-            cntv += eq;
-            first = first && !(eq && k < i);
+    if (odd) {
+        // the reference's form, read by read (log(0) = -inf, NaN propagates)
+        double llk = 0.0;
+        for (int r = 0; r < it.U; r++) {
+            double rp = row[0][r];
+#pragma unroll
+            for (int k = 1; k < PM; k++)
+                if (k < it.P) rp += row[k][r];
+            llk += log(rp) * (it.unit_counts ? 1.0 : (double)s.cnt[r]);
         }
-        const int dose = first ? cntv : 0;
-        if (null_prior) acc += LGAMMA_INT[dose + 1];
-        else if (dose > 0) acc += lgDA[ai * (P + 1) + dose] - (LGAMMA_INT[dose + 1] + lgA[ai]);
+        return llk;
     }
-    if (null_prior) {
-        const double ln_perms = LGAMMA_INT[P + 1] - acc;
-        if (!freqs) return ln_perms - (double)P * log_H;
-        double prod = 1.0;
-        for (int i = 0; i < P; i++) prod *= freqs[g.get(i)];
-        return ln_perms + log(prod);
+    const double e = (double)(expo - 1023 * n_fast);
+    return (e * MCHB_LN2_HI + (e * MCHB_LN2_LO + log(mant))) + slow;
+}
+
+// calling/prior.py:116-179 for a sorted genotype: the dosage of an allele is the length of its run
+// and the reference adds the terms at the first copy of every allele, i.e. run by run.
+template <int PM>
+__device__ __forceinline__ double exact_log_prior(const GenoR<PM> &g, const ExactSmem &s, const ExactItem &it) {
+    double acc = 0.0;
+    int run = 1;
+#pragma unroll
+    for (int k = 0; k < PM; k++) {
+        if (k < it.P) {
+            const bool last = (k == it.P - 1) || (g.g[k + 1 < PM ? k + 1 : k] != g.g[k]);
+            if (last) {
+                if (it.null_prior) acc += LGAMMA_INT[run + 1];
+                else acc += s.lgDA[g.g[k] * (it.P + 1) + run] - (LGAMMA_INT[run + 1] + s.lgA[g.g[k]]);
+                run = 1;
+            } else {
+                run += 1;
+            }
+        }
     }
-    return lg_left + acc;
+    if (!it.null_prior) return it.lg_left + acc;
+    const double ln_perms = LGAMMA_INT[it.P + 1] - acc;
+    if (!it.has_freqs) return ln_perms - it.p_log_h;
+    double prod = 1.0;
+#pragma unroll
+    for (int k = 0; k < PM; k++)
+        if (k < it.P) prod *= s.fr[g.g[k]];
+    return ln_perms + log(prod);
+}
+
+// prior tables of an item (cooperative) -> lg_left; call between barriers
+__device__ __forceinline__ double exact_prior_tables(const ExactSmem &s, int H, int P, double inbreeding,
+                                                     const double *freqs, int tid, int nthr) {
+    for (int i = tid; i < H; i += nthr) s.fr[i] = freqs ? freqs[i] : 0.0;
+    if (isnan(inbreeding) || inbreeding == 0.0) return 0.0;
+    const double scale = (1.0 - inbreeding) / inbreeding;
+    const double alpha_const = (1.0 / (double)H) * scale;
+    for (int i = tid; i < H * (P + 1); i += nthr) {
+        const int al = i / (P + 1), d = i - al * (P + 1);
+        const double alpha = freqs ? freqs[al] * scale : alpha_const;
+        if (d == 0) s.lgA[al] = lgamma(alpha);
+        else s.lgDA[al * (P + 1) + d] = lgamma((double)d + alpha);
+    }
+    double sum_alphas = 0.0;
+    if (freqs) for (int al = 0; al < H; al++) sum_alphas += freqs[al] * scale;
+    else sum_alphas = alpha_const * (double)H;
+    return (LGAMMA_INT[P + 1] + lgamma(sum_alphas)) - lgamma((double)P + sum_alphas);
 }
 
 struct ModeRec {
@@ -141,22 +271,46 @@ __device__ __forceinline__ ModeRec mode_better(const ModeRec &a, const ModeRec &
     return a;
 }
 
+// Fixed-order sum of one value per thread: xor butterfly inside the warp, warps in order.
+__device__ __forceinline__ double block_sum_ordered(double v, double *red, int tid, int nthr) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(MCHB_FULL, v, m);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = red[0];
+    for (int w = 1; w < (nthr >> 5); w++) t += red[w];
+    return t;
+}
+
+// Allele statistics of one genotype with weight p into the thread's partial row:
+// row[2a] += p per copy, row[2a+1] += p once per distinct allele (exact.py:139-148)
+template <int PM>
+__device__ __forceinline__ void exact_tally(const GenoR<PM> &g, int P, double p, double *row) {
+#pragma unroll
+    for (int k = 0; k < PM; k++) {
+        if (k < P) {
+            double *e = row + 2 * g.g[k];
+            e[0] += p;
+            if (k == 0 || g.g[k] != g.g[k > 0 ? k - 1 : 0]) e[1] += p;
+        }
+    }
+}
+
+// PM: register slots of a genotype; FIXED: every item of the launch has ploidy == PM (the slot
+// loops carry no predicates); RECOMP: no parked log joints, the second pass evaluates them again.
+template <int PM, bool FIXED, bool RECOMP>
 __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    // shared layout
-    double *tab = reinterpret_cast<double *>(smem_raw);             // [umax][hmax]
-    double *cnt = tab + (size_t)a.umax * a.hmax;                     // [umax]
-    double *lgA = cnt + a.umax;                                      // [hmax]
-    double *lgDA = lgA + a.hmax;                                     // [hmax][pmax+1]
-    double *sfreq = lgDA + (size_t)a.hmax * (a.pmax + 1);            // [hmax]
-    double *soccur = sfreq + a.hmax;                                 // [hmax]
-    double *red_d = soccur + a.hmax;                                 // [8] reductions
-    ModeRec *red_m = reinterpret_cast<ModeRec *>(red_d + 8);         // [4]
+    const ExactSmem s = exact_carve(smem_raw, a.umax, a.hmax, a.pmax, a.part_threads);
+    const int cstride = a.pmax + 1;
+    ModeRec *red_m = reinterpret_cast<ModeRec *>(s.red + 8);  // [4]
     __shared__ int s_item;
-    double *scratch = a.scratch ? a.scratch + (size_t)blockIdx.x * a.scratch_stride : nullptr;
+    __shared__ int s_tabHP;  // (H << 8) | P the binomial table was filled for
+    double *scratch = RECOMP ? nullptr : a.scratch + (size_t)blockIdx.x * a.scratch_stride;
+    if (tid == 0) s_tabHP = -1;
 
     for (;;) {
         __syncthreads();
@@ -164,51 +318,48 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
         __syncthreads();
         const int item = s_item;
         if (item >= a.n_items) break;
-        const mchb_call_item it = a.items[item];
-        const int U = it.n_reads, N = it.n_pos, A = it.max_allele, P = it.ploidy, H = it.n_haps;
-        const double *R = a.reads + it.reads_off;
-        const int8_t *haps = a.haplotypes + it.haps_off;
-        const double *freqs = (a.freqs && it.freqs_off >= 0) ? a.freqs + it.freqs_off : nullptr;
-        const bool has_prior = !isnan(it.inbreeding);
-        const double inbreeding = it.inbreeding;
+        const mchb_call_item itd = a.items[item];
+        const int U = itd.n_reads, N = itd.n_pos, A = itd.max_allele, H = itd.n_haps;
+        const int P = FIXED ? PM : itd.ploidy;
+        const double *R = a.reads + itd.reads_off;
+        const int8_t *haps = a.haplotypes + itd.haps_off;
+        const double *freqs = (a.freqs && itd.freqs_off >= 0) ? a.freqs + itd.freqs_off : nullptr;
         const double dP = (double)P;
-        const long long G = comb_exact((long long)H + P - 1, P);
+        ExactItem it;
+        it.U = U;
+        it.P = P;
+        it.H = H;
+        it.has_prior = !isnan(itd.inbreeding);
+        it.null_prior = !(it.has_prior && itd.inbreeding != 0.0);
+        it.has_freqs = freqs != nullptr;
+        it.p_log_h = dP * log((double)H);
 
-        // ---- 1. table t[r][h] (likelihood.py:48-60 per haplotype) and counts
+        // ---- 1. table t[h][r] (likelihood.py:48-60 per haplotype), counts, binomials, prior tables
         for (int i = tid; i < U * H; i += nthr) {
-            const int r = i / H, h = i - r * H;
+            const int h = i / U, r = i - h * U;
             double prod = 1.0;
             for (int j = 0; j < N; j++) {
                 double v = __ldg(R + ((size_t)r * N + j) * A + haps[h * N + j]);
                 if (!isnan(v)) prod *= v;
             }
-            tab[r * H + h] = prod / dP;
+            s.tab[h * s.us + r] = prod / dP;
         }
-        for (int r = tid; r < U; r += nthr) cnt[r] = a.counts ? (double)__ldg(a.counts + it.counts_off + r) : 1.0;
-        // ---- prior tables
-        double lg_left = 0.0;
-        const double log_H = log((double)H);
-        if (has_prior && inbreeding != 0.0) {
-            const double scale = (1.0 - inbreeding) / inbreeding;
-            const double alpha_const = (1.0 / (double)H) * scale;
-            for (int i = tid; i < H * (P + 1); i += nthr) {
-                const int al = i / (P + 1), d = i - al * (P + 1);
-                const double alpha = freqs ? freqs[al] * scale : alpha_const;
-                if (d == 0) lgA[al] = lgamma(alpha);
-                else lgDA[al * (P + 1) + d] = lgamma((double)d + alpha);
-            }
-            double sum_alphas = 0.0;
-            if (freqs) for (int al = 0; al < H; al++) sum_alphas += freqs[al] * scale;
-            else sum_alphas = alpha_const * (double)H;
-            lg_left = (LGAMMA_INT[P + 1] + lgamma(sum_alphas)) - lgamma(dP + sum_alphas);
+        int not_unit = 0;
+        for (int r = tid; r < U; r += nthr) {
+            const long long c = a.counts ? __ldg(a.counts + itd.counts_off + r) : 1;
+            s.cnt[r] = (int)c;
+            not_unit |= (c != 1);
         }
-        for (int i = tid; i < H; i += nthr) {
-            sfreq[i] = 0.0;
-            soccur[i] = 0.0;
+        it.unit_counts = !__syncthreads_or(not_unit);
+        if (s_tabHP != ((H << 8) | P)) {  // uniform: read before the barrier inside the fill
+            exact_fill_cwr(s.cwr, H, P, cstride, tid, nthr);
+            if (tid == 0) s_tabHP = (H << 8) | P;
         }
+        it.lg_left = exact_prior_tables(s, H, P, itd.inbreeding, freqs, tid, nthr);
         __syncthreads();
+        const long long G = s.cwr[H * cstride + P];
 
-        // ---- 2. enumerate this thread's chunk of genotypes in VCF order
+        // ---- 2. first pass over this thread's chunk of genotypes in VCF order
         const long long chunk = (G + nthr - 1) / nthr;
         const long long g0 = (long long)tid * chunk;
         const long long g1 = g0 + chunk < G ? g0 + chunk : G;
@@ -216,32 +367,23 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
         best.ljoint = -INFINITY;
         best.llk = -INFINITY;
         best.idx = 0x7fffffffffffffffLL;
-        double total = -INFINITY;
         if (g0 < G) {
-            Geno g = geno_unrank(g0, P);
+            GenoR<PM> g;
+            g.unrank(g0, P, s.cwr, cstride, H);
             for (long long gi = g0; gi < g1; gi++) {
-                double llk = 0.0;
-                for (int r = 0; r < U; r++) {
-                    const double *row = tab + r * H;
-                    double rp = 0.0;
-                    for (int k = 0; k < P; k++) rp += row[g.get(k)];
-                    llk += log(rp) * cnt[r];
-                }
+                const double llk = exact_llk<PM>(g, s, it);
                 if (a.mode == 1) {
-                    a.out_gl[it.gl_off + gi] = (float)llk;
+                    a.out_gl[itd.gl_off + gi] = (float)llk;
                 } else {
-                    double lpr = 0.0;
-                    if (has_prior) lpr = exact_log_prior(g, P, H, inbreeding, freqs, lgA, lgDA, lg_left, log_H);
-                    const double ljoint = llk + lpr;
+                    const double ljoint = llk + (it.has_prior ? exact_log_prior<PM>(g, s, it) : 0.0);
                     if (ljoint > best.ljoint) {
                         best.ljoint = ljoint;
                         best.llk = llk;
                         best.idx = gi;
                     }
-                    total = add_log_prob(total, ljoint);
-                    scratch[gi] = ljoint;
+                    if (!RECOMP) scratch[gi] = ljoint;
                 }
-                geno_increment(g, P);
+                g.increment(P);
             }
         }
         if (a.mode == 1) {
@@ -255,7 +397,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
             }
             continue;
         }
-        // ---- 3. block reductions: first maximum and log-sum-exp
+        // ---- 3. first maximum over the block
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
             ModeRec o;
@@ -263,52 +405,84 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
             o.llk = __shfl_xor_sync(MCHB_FULL, best.llk, m);
             o.idx = __shfl_xor_sync(MCHB_FULL, best.idx, m);
             best = mode_better(best, o);
-            total = add_log_prob(total, __shfl_xor_sync(MCHB_FULL, total, m));
         }
-        if (lane == 0) {
-            red_m[warp] = best;
-            red_d[warp] = total;
-        }
-        __syncthreads();
-        const int nwarp = nthr >> 5;
+        if ((tid & 31) == 0) red_m[tid >> 5] = best;
+        __syncthreads();  // also: every log joint of the first pass is in scratch
         best = red_m[0];
-        total = red_d[0];
-        for (int w = 1; w < nwarp; w++) {
-            best = mode_better(best, red_m[w]);
-            total = add_log_prob(total, red_d[w]);
-        }
+        for (int w = 1; w < (nthr >> 5); w++) best = mode_better(best, red_m[w]);
         if (!(best.ljoint > -INFINITY)) {  // nothing ever exceeded -inf: the reference keeps index 0
             best.idx = 0;
             best.llk = -INFINITY;
             best.ljoint = -INFINITY;
         }
-        // ---- 4. mode alleles, support probability (thread 0), then allele statistics (all)
+        const double top = best.ljoint;
+        // ---- 4. second pass: sum of exp(ljoint - top) and the allele statistics in per-thread rows
+        const int pt = a.part_threads;
+        double ssum = 0.0;
+        if (tid < pt) {
+            double *row = s.part + (size_t)tid * s.hs * 2;
+            for (int i = 0; i < 2 * H; i++) row[i] = 0.0;
+            const long long chunk2 = (G + pt - 1) / pt;
+            const long long b0 = (long long)tid * chunk2;
+            const long long b1 = b0 + chunk2 < G ? b0 + chunk2 : G;
+            if (b0 < G) {
+                GenoR<PM> g;
+                g.unrank(b0, P, s.cwr, cstride, H);
+                for (long long gi = b0; gi < b1; gi++) {
+                    double lj;
+                    if (!RECOMP) lj = scratch[gi];
+                    else lj = exact_llk<PM>(g, s, it) + (it.has_prior ? exact_log_prior<PM>(g, s, it) : 0.0);
+                    const double p = exp(lj - top);
+                    ssum += p;
+                    exact_tally<PM>(g, P, p, row);
+                    g.increment(P);
+                }
+            }
+        }
+        const double stot = block_sum_ordered(ssum, s.red, tid, nthr);
+        const double total = top + log(stot);
+        // ---- 5. outputs: allele statistics (partial rows added in thread order), mode, support
+        for (int i = tid; i < 2 * H; i += nthr) {
+            double acc = 0.0;
+            for (int t = 0; t < pt; t++) acc += s.part[(size_t)t * s.hs * 2 + i];
+            const double v = acc / stot;
+            if (i & 1) a.out_occur[itd.hap_out_off + (i >> 1)] = v;
+            else a.out_freqs[itd.hap_out_off + (i >> 1)] = v / dP;
+        }
         if (tid == 0) {
-            const Geno mode = geno_unrank(best.idx, P);
-            for (int k = 0; k < P; k++) a.out_alleles[(size_t)item * a.pstride + k] = mode.get(k);
+            GenoR<PM> mode;
+            mode.unrank(best.idx, P, s.cwr, cstride, H);
+#pragma unroll
+            for (int k = 0; k < PM; k++)
+                if (k < P) a.out_alleles[(size_t)item * a.pstride + k] = mode.g[k];
             for (int k = P; k < a.pstride; k++) a.out_alleles[(size_t)item * a.pstride + k] = -2;
             // exact.py:64-105: all dosage variants of the mode's haplotype set, in
             // combinations_with_replacement order
             int support[MCHB_MAX_PLOIDY];
             int ns = 0;
-            for (int k = 0; k < P; k++)
-                if (k == 0 || mode.get(k) != mode.get(k - 1)) support[ns++] = mode.get(k);
+#pragma unroll
+            for (int k = 0; k < PM; k++)
+                if (k < P && (k == 0 || mode.g[k] != mode.g[k > 0 ? k - 1 : 0])) support[ns++] = mode.g[k];
             const int rem = P - ns;
             int idx[MCHB_MAX_PLOIDY];
             for (int k = 0; k < rem; k++) idx[k] = 0;
             double support_ljoint = -INFINITY;
             for (;;) {
                 // merge support + chosen extras into a sorted genotype (counting sort over support)
-                Geno t;
-                t.lo = 0;
-                t.hi = 0;
+                int merged[MCHB_MAX_PLOIDY];
                 int pos = 0;
-                for (int s = 0; s < ns; s++) {
+                for (int q = 0; q < ns; q++) {
                     int c = 1;
-                    for (int k = 0; k < rem; k++) c += (idx[k] == s);
-                    for (int k = 0; k < c; k++) t.set(pos++, support[s]);
+                    for (int k = 0; k < rem; k++) c += (idx[k] == q);
+                    for (int k = 0; k < c; k++) merged[pos++] = support[q];
                 }
-                support_ljoint = add_log_prob(support_ljoint, scratch[geno_rank(t, P)]);
+                GenoR<PM> t;
+#pragma unroll
+                for (int k = 0; k < PM; k++) t.g[k] = k < P ? merged[k] : 0;
+                double lj;
+                if (!RECOMP) lj = scratch[t.rank(P, s.cwr, cstride)];
+                else lj = exact_llk<PM>(t, s, it) + (it.has_prior ? exact_log_prior<PM>(t, s, it) : 0.0);
+                support_ljoint = add_log_prob(support_ljoint, lj);
                 int i = rem - 1;
                 while (i >= 0 && idx[i] == ns - 1) i--;
                 if (i < 0) break;
@@ -320,26 +494,6 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
             st[1] = exp(best.ljoint - total);
             st[2] = exp(support_ljoint - total);
             st[3] = total;
-        }
-        __syncthreads();  // scratch complete and visible
-        if (g0 < G) {
-            Geno g = geno_unrank(g0, P);
-            for (long long gi = g0; gi < g1; gi++) {
-                const double prob = exp(scratch[gi] - total);
-                for (int k = 0; k < P; k++) {
-                    const int al = g.get(k);
-                    atomicAdd(&sfreq[al], prob);
-                    if (k == 0 || al != g.get(k - 1)) atomicAdd(&soccur[al], prob);
-                }
-                geno_increment(g, P);
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < H; i += nthr) {
-            a.out_freqs[it.hap_out_off + i] = sfreq[i] / dP;
-            a.out_occur[it.hap_out_off + i] = soccur[i];
-        }
-        if (tid == 0) {
             mchb_item_result r;
             r.status = MCHB_ITEM_OK;
             r.n_het = 0;
@@ -354,6 +508,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
 // item per CTA from a stored llk array (float32 as the reference's CLI branch stores it, or
 // float64).  posteriors[i] = exp(x_i - logsumexp(x)), x_i = STORED(llk_i + lprior_i) where the
 // store rounds to float32 when the input was float32 (numba keeps the array dtype, exact.py:311).
+// Same enumeration, prior and fixed-order reductions as exact_kernel.
 struct PosteriorArgs {
     const mchb_call_item *items;
     int32_t n_items;
@@ -365,91 +520,109 @@ struct PosteriorArgs {
     double *out_counts;
     double *out_occur;
     int32_t hmax, pmax;
+    int32_t part_threads;
 };
 
+template <int PM>
 __global__ void __launch_bounds__(128) posterior_kernel(const __grid_constant__ PosteriorArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    double *lgA = reinterpret_cast<double *>(smem_raw);
-    double *lgDA = lgA + a.hmax;
-    double *sfreq = lgDA + (size_t)a.hmax * (a.pmax + 1);
-    double *soccur = sfreq + a.hmax;
-    double *red_d = soccur + a.hmax;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const ExactSmem s = exact_carve(smem_raw, 0, a.hmax, a.pmax, a.part_threads);
+    const int cstride = a.pmax + 1;
+    __shared__ int s_tabHP;
+    if (tid == 0) s_tabHP = -1;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         __syncthreads();
-        const mchb_call_item it = a.items[item];
-        const int P = it.ploidy, H = it.n_haps;
-        const double *freqs = (a.freqs && it.freqs_off >= 0) ? a.freqs + it.freqs_off : nullptr;
-        const bool has_prior = !isnan(it.inbreeding);
-        const double inbreeding = it.inbreeding;
+        const mchb_call_item itd = a.items[item];
+        const int P = itd.ploidy, H = itd.n_haps;
+        const double *freqs = (a.freqs && itd.freqs_off >= 0) ? a.freqs + itd.freqs_off : nullptr;
         const double dP = (double)P;
-        const long long G = comb_exact((long long)H + P - 1, P);
-        double lg_left = 0.0;
-        const double log_H = log((double)H);
-        if (has_prior && inbreeding != 0.0) {
-            const double scale = (1.0 - inbreeding) / inbreeding;
-            const double alpha_const = (1.0 / (double)H) * scale;
-            for (int i = tid; i < H * (P + 1); i += nthr) {
-                const int al = i / (P + 1), d = i - al * (P + 1);
-                const double alpha = freqs ? freqs[al] * scale : alpha_const;
-                if (d == 0) lgA[al] = lgamma(alpha);
-                else lgDA[al * (P + 1) + d] = lgamma((double)d + alpha);
-            }
-            double sum_alphas = 0.0;
-            if (freqs) for (int al = 0; al < H; al++) sum_alphas += freqs[al] * scale;
-            else sum_alphas = alpha_const * (double)H;
-            lg_left = (LGAMMA_INT[P + 1] + lgamma(sum_alphas)) - lgamma(dP + sum_alphas);
+        ExactItem it;
+        it.U = 0;
+        it.P = P;
+        it.H = H;
+        it.unit_counts = true;
+        it.has_prior = !isnan(itd.inbreeding);
+        it.null_prior = !(it.has_prior && itd.inbreeding != 0.0);
+        it.has_freqs = freqs != nullptr;
+        it.p_log_h = dP * log((double)H);
+        if (s_tabHP != ((H << 8) | P)) {
+            exact_fill_cwr(s.cwr, H, P, cstride, tid, nthr);
+            if (tid == 0) s_tabHP = (H << 8) | P;
         }
-        for (int i = tid; i < H; i += nthr) {
-            sfreq[i] = 0.0;
-            soccur[i] = 0.0;
-        }
+        it.lg_left = exact_prior_tables(s, H, P, itd.inbreeding, freqs, tid, nthr);
         __syncthreads();
+        const long long G = s.cwr[H * cstride + P];
         const long long chunk = (G + nthr - 1) / nthr;
         const long long g0 = (long long)tid * chunk;
         const long long g1 = g0 + chunk < G ? g0 + chunk : G;
-        double *gp = a.out_gp + it.gl_off;
-        double total = -INFINITY;
+        double *gp = a.out_gp + itd.gl_off;
+        // ---- log joints (stored like the reference stores them) and their maximum
+        double top = -INFINITY;
+        bool any_nan = false;
         if (g0 < G) {
-            Geno g = geno_unrank(g0, P);
+            GenoR<PM> g;
+            g.unrank(g0, P, s.cwr, cstride, H);
             for (long long gi = g0; gi < g1; gi++) {
-                double lpr = 0.0;
-                if (has_prior) lpr = exact_log_prior(g, P, H, inbreeding, freqs, lgA, lgDA, lg_left, log_H);
+                const double lpr = it.has_prior ? exact_log_prior<PM>(g, s, it) : 0.0;
                 double x;
-                if (a.llk32) x = (double)(float)((double)a.llk32[it.gl_off + gi] + lpr);
-                else x = a.llk64[it.gl_off + gi] + lpr;
+                if (a.llk32) x = (double)(float)((double)a.llk32[itd.gl_off + gi] + lpr);
+                else x = a.llk64[itd.gl_off + gi] + lpr;
                 gp[gi] = x;
-                total = add_log_prob(total, x);
-                geno_increment(g, P);
+                any_nan = any_nan || isnan(x);
+                if (x > top) top = x;
+                g.increment(P);
             }
         }
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) total = add_log_prob(total, __shfl_xor_sync(MCHB_FULL, total, m));
-        if (lane == 0) red_d[warp] = total;
+        for (int m = 16; m > 0; m >>= 1) top = fmax(top, __shfl_xor_sync(MCHB_FULL, top, m));
         __syncthreads();
-        total = red_d[0];
-        for (int w = 1; w < (nthr >> 5); w++) total = add_log_prob(total, red_d[w]);
-        if (g0 < G) {
-            Geno g = geno_unrank(g0, P);
-            for (long long gi = g0; gi < g1; gi++) {
-                const double prob = exp(gp[gi] - total);
-                gp[gi] = prob;
-                if (a.out_freqs) {
-                    for (int k = 0; k < P; k++) {
-                        const int al = g.get(k);
-                        atomicAdd(&sfreq[al], prob);
-                        if (k == 0 || al != g.get(k - 1)) atomicAdd(&soccur[al], prob);
-                    }
-                }
-                geno_increment(g, P);
-            }
+        if ((tid & 31) == 0) s.red[8 + (tid >> 5)] = top;
+        const int has_nan = __syncthreads_or(any_nan);
+        top = s.red[8];
+        for (int w = 1; w < (nthr >> 5); w++) top = fmax(top, s.red[8 + w]);
+        if (has_nan) top = NAN;  // the reference's fold propagates NaN to every posterior
+        // ---- normaliser: sum of exp(x - top) in fixed order
+        double ssum = 0.0;
+        for (long long gi = g0; gi < g1; gi++) {
+            const double p = exp(gp[gi] - top);
+            gp[gi] = p;
+            ssum += p;
         }
+        const double stot = block_sum_ordered(ssum, s.red, tid, nthr);
+        // exp(x - (top + log(stot))) evaluated as exp(x - top) / stot
+        const int pt = a.part_threads;
+        if (a.out_freqs && tid < pt) {
+            double *row = s.part + (size_t)tid * s.hs * 2;
+            for (int i = 0; i < 2 * H; i++) row[i] = 0.0;
+        }
+        for (long long gi = g0; gi < g1; gi++) gp[gi] = gp[gi] / stot;
         __syncthreads();
         if (a.out_freqs) {
-            for (int i = tid; i < H; i += nthr) {
-                a.out_freqs[it.hap_out_off + i] = sfreq[i] / dP;
-                a.out_counts[it.hap_out_off + i] = sfreq[i];
-                a.out_occur[it.hap_out_off + i] = soccur[i];
+            if (tid < pt) {
+                double *row = s.part + (size_t)tid * s.hs * 2;
+                const long long chunk2 = (G + pt - 1) / pt;
+                const long long b0 = (long long)tid * chunk2;
+                const long long b1 = b0 + chunk2 < G ? b0 + chunk2 : G;
+                if (b0 < G) {
+                    GenoR<PM> g;
+                    g.unrank(b0, P, s.cwr, cstride, H);
+                    for (long long gi = b0; gi < b1; gi++) {
+                        exact_tally<PM>(g, P, gp[gi], row);
+                        g.increment(P);
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < 2 * H; i += nthr) {
+                double acc = 0.0;
+                for (int t = 0; t < pt; t++) acc += s.part[(size_t)t * s.hs * 2 + i];
+                if (i & 1) {
+                    a.out_occur[itd.hap_out_off + (i >> 1)] = acc;
+                } else {
+                    a.out_freqs[itd.hap_out_off + (i >> 1)] = acc / dP;
+                    a.out_counts[itd.hap_out_off + (i >> 1)] = acc;
+                }
             }
         }
     }

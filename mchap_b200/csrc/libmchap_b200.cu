@@ -4,6 +4,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 //             -Xcompiler -fPIC -shared -cudart static
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <map>
@@ -852,7 +853,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
 namespace {
 
 struct CallGeom {
-    int umax = 1, hmax = 1, pmax = 1;
+    int umax = 1, hmax = 1, pmax = 1, pmin = 1 << 30;
     long long gmax = 1;
 };
 
@@ -888,15 +889,53 @@ int check_call_items(mchb_handle *h, const mchb_call_item *items, int64_t n_item
         g.umax = std::max(g.umax, it.n_reads);
         g.hmax = std::max(g.hmax, it.n_haps);
         g.pmax = std::max(g.pmax, it.ploidy);
+        g.pmin = std::min(g.pmin, it.ploidy);
         g.gmax = std::max(g.gmax, G);
     }
     return MCHB_OK;
 }
 
-size_t exact_smem(const CallGeom &g) {
-    size_t d = (size_t)g.umax * g.hmax + g.umax + g.hmax + (size_t)g.hmax * (g.pmax + 1) + 2 * (size_t)g.hmax + 8;
-    return d * 8 + 4 * sizeof(ModeRec) + 64;
+// threads of a CTA that own a partial row of allele statistics: as many as fit 32 KB
+int exact_part_threads(const CallGeom &g) {
+    int pt = 128;
+    while (pt > 1 && (size_t)pt * (g.hmax | 1) * 16 > 32768) pt >>= 1;
+    return pt;
 }
+
+// host mirror of exact_carve()
+size_t exact_smem(const CallGeom &g, int umax, int part_threads) {
+    const size_t us = (size_t)(umax | 1), hs = (size_t)(g.hmax | 1);
+    size_t d = (size_t)g.hmax * us + g.hmax + (size_t)g.hmax * (g.pmax + 1) + g.hmax + (size_t)part_threads * hs * 2 + 32 +
+               (size_t)(g.hmax + 1) * (g.pmax + 1);
+    return d * 8 + (size_t)umax * 4 + 64;
+}
+
+// Instantiations of exact_kernel: ploidies 2, 4, 6, 8 have kernels specialised for batches in which
+// every item has that ploidy; anything else (mixed or odd ploidies, ploidy > 8, or no room for parked
+// log joints) runs the generic 16-slot kernel.
+#define MCHB_EXACT_DISPATCH(fixed_p, recomp, CALL)                  \
+    do {                                                            \
+        if (recomp) { CALL(16, false, true); }                      \
+        else if ((fixed_p) == 2) { CALL(2, true, false); }          \
+        else if ((fixed_p) == 4) { CALL(4, true, false); }          \
+        else if ((fixed_p) == 6) { CALL(6, true, false); }          \
+        else if ((fixed_p) == 8) { CALL(8, true, false); }          \
+        else { CALL(16, false, false); }                            \
+    } while (0)
+
+// posterior_kernel: smallest compiled slot count >= pmax
+#define MCHB_POSTERIOR_DISPATCH(pmax, CALL) \
+    do {                                    \
+        if ((pmax) <= 4) { CALL(4); }       \
+        else if ((pmax) <= 8) { CALL(8); }  \
+        else { CALL(16); }                  \
+    } while (0)
+
+// bytes of parked log joints the whole grid may hold (mchb_call_exact_mode_batch); beyond it the
+// grid shrinks, and an item too large for a single row is evaluated twice instead
+#ifndef MCHB_EXACT_SCRATCH_BUDGET
+#define MCHB_EXACT_SCRATCH_BUDGET (2ull << 30)
+#endif
 
 int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, int64_t n_items, const double *reads,
               int64_t reads_len, const int64_t *counts, int64_t counts_len, const int8_t *haplotypes,
@@ -919,7 +958,8 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
         h->err = "pstride smaller than the largest ploidy";
         return MCHB_ERR_ARGUMENT;
     }
-    const size_t smem = exact_smem(g);
+    const int part_threads = exact_part_threads(g);
+    const size_t smem = exact_smem(g, g.umax, part_threads);
     if (smem > (size_t)h->smem_optin) {
         h->err = "call-exact item needs more shared memory than one CTA can have";
         return MCHB_ERR_ARGUMENT;
@@ -937,9 +977,18 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
     if ((rc = stage_in(h, mem, S_COUNTS, counts, counts_len, &dcounts))) return rc;
     if ((rc = stage_in(h, mem, S_HAPS, haplotypes, haplotypes_len, &dhaps))) return rc;
     if ((rc = stage_in(h, mem, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
-    CK(cudaFuncSetAttribute(exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exact_kernel, 128, smem));
+    // one ploidy for the whole batch -> specialised kernel; parked log joints need a row per CTA
+    const int fixed_p = (g.pmin == g.pmax) ? g.pmax : 0;
+    const unsigned long long row_bytes = sizeof(double) * (unsigned long long)g.gmax;
+    unsigned long long budget = MCHB_EXACT_SCRATCH_BUDGET;
+    if (const char *env = getenv("MCHB_EXACT_SCRATCH_BYTES")) budget = strtoull(env, nullptr, 10);  // tests: force the low-memory path
+    const bool recomp = mode == 0 && row_bytes > budget;
+#define EXACT_PREP(PM, FIXED, RECOMP)                                                                                   \
+    CK(cudaFuncSetAttribute(exact_kernel<PM, FIXED, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exact_kernel<PM, FIXED, RECOMP>, 128, smem))
+    MCHB_EXACT_DISPATCH(fixed_p, recomp, EXACT_PREP);
+#undef EXACT_PREP
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     long long grid = std::min<long long>(n_items, (long long)h->sm_count * ctas_per_sm);
     ExactArgs a;
@@ -957,14 +1006,19 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
     a.hmax = g.hmax;
     a.pmax = g.pmax;
     a.pstride = pstride;
+    a.part_threads = part_threads;
     int64_t *dalleles = nullptr;
     double *dstats = nullptr, *dfo = nullptr, *doc = nullptr;
     float *dgl = nullptr;
     if (mode == 0) {
-        void *scratch;
-        if ((rc = ensure(h, S_SCRATCH, sizeof(double) * (size_t)grid * (size_t)g.gmax, &scratch))) return rc;
-        a.scratch = (double *)scratch;
-        a.scratch_stride = g.gmax;
+        // parked log joints: one row of gmax doubles per CTA, inside the budget
+        if (!recomp) {
+            grid = std::max<long long>(1, std::min<long long>(grid, (long long)(budget / row_bytes)));
+            void *scratch;
+            if ((rc = ensure(h, S_SCRATCH, (size_t)row_bytes * (size_t)grid, &scratch))) return rc;
+            a.scratch = (double *)scratch;
+            a.scratch_stride = g.gmax;
+        }  // else: a.scratch stays null and the second pass evaluates the log joints again
         if ((rc = stage_out(h, mem, S_OUT_A, out_alleles, n_items * pstride, &dalleles))) return rc;
         if ((rc = stage_out(h, mem, S_OUT_S, out_stats, n_items * 4, &dstats))) return rc;
         if ((rc = stage_out(h, mem, S_OUT_F, out_freqs, hap_out_len, &dfo))) return rc;
@@ -978,7 +1032,9 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
         a.out_gl = dgl;
     }
     CK(cudaEventRecord(h->ev0, h->stream));
-    exact_kernel<<<(unsigned)grid, 128, smem, h->stream>>>(a);
+#define EXACT_LAUNCH(PM, FIXED, RECOMP) exact_kernel<PM, FIXED, RECOMP><<<(unsigned)grid, 128, smem, h->stream>>>(a)
+    MCHB_EXACT_DISPATCH(fixed_p, recomp, EXACT_LAUNCH);
+#undef EXACT_LAUNCH
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches++;
@@ -1035,7 +1091,8 @@ int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item
     int rc = check_call_items(h, items, n_items, 0, false, 0, 0, freqs != nullptr, freqs_len, out_freqs ? hap_out_len : -1,
                               gl_len, false, g);
     if (rc) return rc;
-    const size_t smem = ((size_t)g.hmax * (g.pmax + 4) + 16) * 8;
+    const int part_threads = exact_part_threads(g);
+    const size_t smem = exact_smem(g, 0, part_threads);
     void *ditems;
     if ((rc = ensure(h, S_ITEMS, sizeof(mchb_call_item) * (size_t)n_items, &ditems))) return rc;
     CK(cudaMemcpyAsync(ditems, items, sizeof(mchb_call_item) * (size_t)n_items, cudaMemcpyHostToDevice, h->stream));
@@ -1048,6 +1105,7 @@ int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item
     a.freqs = dfreqs;
     a.hmax = g.hmax;
     a.pmax = g.pmax;
+    a.part_threads = part_threads;
     if (llk_is_f32) {
         const float *d;
         if ((rc = stage_in(h, mem, S_LLKS, (const float *)llks, gl_len, &d))) return rc;
@@ -1068,10 +1126,14 @@ int mchb_genotype_posteriors_batch(mchb_handle *h, int mem, const mchb_call_item
         a.out_counts = dco;
         a.out_occur = doc;
     }
-    CK(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = std::min<long long>(n_items, (long long)h->sm_count * 8);
+#define POST_PREP(PM) CK(cudaFuncSetAttribute(posterior_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+    MCHB_POSTERIOR_DISPATCH(g.pmax, POST_PREP);
+#undef POST_PREP
     CK(cudaEventRecord(h->ev0, h->stream));
-    posterior_kernel<<<(unsigned)grid, 128, smem, h->stream>>>(a);
+#define POST_LAUNCH(PM) posterior_kernel<PM><<<(unsigned)grid, 128, smem, h->stream>>>(a)
+    MCHB_POSTERIOR_DISPATCH(g.pmax, POST_LAUNCH);
+#undef POST_LAUNCH
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->launches++;

@@ -370,6 +370,133 @@ def test_calling_mcmc_golden(dev, golden):
         assert trace.n_allele == len(haps)
 
 
+def _exact_case(n_items, n_haps, n_pos, ploidies, depth, seed, counts_scale=1):
+    from mchap_b200.synth import synth_haplotype_panel
+
+    pmax = int(np.max(ploidies))
+    batch, panels, _ = synth_haplotype_panel(n_items, n_haps, n_pos, pmax, depth=depth, seed=seed)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] * counts_scale for i in range(n_items)]
+    return reads, counts, [panels[i] for i in range(n_items)]
+
+
+def test_call_exact_mixed_ploidy_counts_and_reproducibility(dev, oracle):
+    """Odd / mixed ploidies run the generic kernel; read counts above the product-form limit take
+    log(rp) * count; zero reads; two runs of the same batch are bit-identical (fixed-order reductions)."""
+    from mchap_b200.calling import exact
+
+    ploidies = np.array([3, 5, 2, 7, 4, 6, 1, 3, 9, 4])
+    reads, counts, haps = _exact_case(len(ploidies), 6, 5, ploidies, 30, 91)
+    counts[1] = counts[1] * 40          # counts far above MCHB_EXACT_POW_MAX
+    counts[4] = counts[4] * 16 + 1      # straddles the limit
+    reads[7] = reads[7][:0]             # no reads at all: posterior = prior
+    counts[7] = counts[7][:0]
+    rng = np.random.default_rng(3)
+    priors = []
+    for i in range(len(ploidies)):
+        f = rng.random(6) + 0.05
+        priors.append([None, (0.15, None), (0.3, f / f.sum()), (0.0, f / f.sum())][i % 4])
+    first = exact.posterior_mode_batch(reads, ploidies, haps, counts, priors)
+    again = exact.posterior_mode_batch(reads, ploidies, haps, counts, priors)
+    for i, P in enumerate(ploidies):
+        want = oracle.posterior_mode(reads[i], int(P), haps[i], counts[i], priors[i], True, True, True)
+        got = first[i]
+        np.testing.assert_array_equal(got[0], want[0], err_msg="item %d" % i)
+        close([got[1], got[2], got[3]], [want[1], want[2], want[3]])
+        close(got[4], want[4])
+        close(got[5], want[5])
+        for x, y in zip(got, again[i]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y))   # bit-identical reruns
+    gls = exact.genotype_likelihoods_batch(reads, ploidies, haps, counts)
+    for i, P in enumerate(ploidies):
+        gl64 = oracle.genotype_likelihoods(reads[i], int(P), haps[i], counts[i], dtype=np.float64)
+        np.testing.assert_allclose(gls[i], gl64.astype(np.float32), rtol=2e-7, atol=0)
+
+
+def test_call_exact_impossible_reads(dev, oracle):
+    """Per-read probabilities that are exactly zero: a read no allele can produce makes every genotype
+    -inf (normaliser -inf, NaN posteriors, mode index 0 like the reference); a read only the all-zero
+    haplotype can produce makes the genotypes without that haplotype -inf.  These leave the
+    product form and take the reference's log(rp) * count."""
+    from mchap_b200.calling import exact
+
+    reads, counts, haps = _exact_case(4, 4, 4, np.array([4, 4, 4, 4]), 12, 5)
+    for i, r in enumerate(reads):
+        r[0, :, :] = 0.0
+        if i % 2:
+            r[0, :, 0] = 1.0
+            haps[i][0, :] = 0
+    res = exact.posterior_mode_batch(reads, 4, haps, counts, None)
+    gls = exact.genotype_likelihoods_batch(reads, 4, haps, counts)
+    for i in range(4):
+        want = oracle.posterior_mode(reads[i], 4, haps[i], counts[i], None, True, True, True)
+        gl64 = oracle.genotype_likelihoods(reads[i], 4, haps[i], counts[i], dtype=np.float64)
+        np.testing.assert_array_equal(res[i][0], want[0])
+        np.testing.assert_allclose(gls[i], gl64.astype(np.float32), rtol=2e-7, atol=0, equal_nan=True)
+        close([res[i][1], res[i][2], res[i][3]], [want[1], want[2], want[3]])
+
+
+def test_call_exact_low_memory_path(dev, oracle, monkeypatch):
+    """No room for parked log joints (one large item must not size a scratch of hundreds of
+    GB): the second pass evaluates the log joints again, like the reference's
+    _posterior_allele_frequencies, and gives the same answers."""
+    from mchap_b200.calling import exact
+
+    reads, counts, haps = _exact_case(6, 8, 8, np.array([6] * 6), 40, 17)
+    priors = [(0.1, None)] * 6
+    parked = exact.posterior_mode_batch(reads, 6, haps, counts, priors)
+    monkeypatch.setenv("MCHB_EXACT_SCRATCH_BYTES", "1024")
+    twice = exact.posterior_mode_batch(reads, 6, haps, counts, priors)
+    for i in range(6):
+        want = oracle.posterior_mode(reads[i], 6, haps[i], counts[i], priors[i], True, True, True)
+        np.testing.assert_array_equal(twice[i][0], want[0])
+        close([twice[i][1], twice[i][2], twice[i][3]], [want[1], want[2], want[3]])
+        close(twice[i][4], want[4])
+        close(twice[i][5], want[5])
+        np.testing.assert_array_equal(twice[i][0], parked[i][0])
+        close(twice[i][4], parked[i][4], rtol=1e-12)
+
+
+def test_genotype_posteriors_batch_vs_oracle(dev, oracle):
+    from mchap_b200.calling import exact
+
+    ploidies = np.array([4, 6, 2, 4, 3])
+    reads, counts, haps = _exact_case(5, 7, 5, ploidies, 25, 23)
+    rng = np.random.default_rng(8)
+    f = rng.random(7) + 0.1
+    priors = [None, (0.1, None), (0.25, f / f.sum()), (0.0, f / f.sum()), (0.4, None)]
+    gls = exact.genotype_likelihoods_batch(reads, ploidies, haps, counts)
+    gps, trips = exact.genotype_posteriors_batch(gls, ploidies, [7] * 5, priors, with_frequencies=True)
+    again, _ = exact.genotype_posteriors_batch(gls, ploidies, [7] * 5, priors, with_frequencies=True)
+    for i, P in enumerate(ploidies):
+        want = oracle.genotype_posteriors(gls[i], int(P), 7, priors[i])
+        np.testing.assert_allclose(gps[i], want, rtol=1e-9, atol=1e-300)
+        wf = oracle.posterior_allele_frequencies(want, int(P), 7)
+        for got, w in zip(trips[i], wf):
+            np.testing.assert_allclose(got, w, rtol=1e-9, atol=1e-300)
+        np.testing.assert_array_equal(gps[i], again[i])
+        one = exact.genotype_posteriors(gls[i], int(P), 7, priors[i])
+        np.testing.assert_array_equal(one, gps[i])
+
+
+def test_minimum_error_correction_batch(dev):
+    rng = np.random.default_rng(12)
+    calls, genos = [], []
+    for i in range(40):
+        R, N, P = int(rng.integers(0, 90)), int(rng.integers(1, 12)), int(rng.integers(1, 9))
+        c = rng.integers(-1, 3, size=(R, N)).astype(np.int8)
+        g = rng.integers(-1, 3, size=(P, N)).astype(np.int8)
+        calls.append(c)
+        genos.append(g)
+    mec, called, rows = dev.minimum_error_correction_batch(calls, genos, per_read=True)
+    for i, (c, g) in enumerate(zip(calls, genos)):
+        # encoding/integer/stats.py:18-39 restated with numpy
+        diff = (c[:, None, :] != g[None, :, :]) & (c[:, None, :] >= 0)
+        want = diff.sum(axis=-1).min(axis=-1)
+        np.testing.assert_array_equal(rows[i], want)
+        assert mec[i] == want.sum() and called[i] == (c >= 0).sum()
+
+
 @pytest.mark.parametrize("ploidy,n_haps,step_type,prior_kind", [
     (4, 32, "Gibbs", None),           # BASELINE configs[4] shape
     (4, 32, "Gibbs", "freqs"),
