@@ -47,7 +47,7 @@ struct ExactArgs {
     double *out_freqs;          // per item at hap_out_off: posterior mean allele frequencies
     double *out_occur;          // per item at hap_out_off: posterior occurrence
     float *out_gl;              // per item at gl_off (mode 1)
-    double *scratch;            // [gridDim.x, scratch_stride] log joints; null: evaluate twice
+    double *scratch;            // [gridDim.x, scratch_stride] log joints, row layout [step][thread]; null: evaluate twice
     int64_t scratch_stride;
     int32_t *work_counter;
     mchb_item_result *results;
@@ -70,22 +70,25 @@ struct ExactSmem {
     double *part;     // [part_threads][hs][2] partial allele statistics
     double *red;      // [32]: [0..7] per-warp sums, [8..] per-warp mode records / maxima
     long long *cwr;   // [(hmax+1)][pmax+1] C(n+p-1, p)
-    int *cnt;         // [umax] read counts
-    int us, hs;
+    int *cnt;         // [umax] read counts in column order
+    int *col;         // [umax] table column of read r
+    int us, hs, ps;   // row strides (doubles): table, -, partial rows (odd: rows of a warp start in different banks)
 };
 
 __device__ __forceinline__ ExactSmem exact_carve(unsigned char *raw, int umax, int hmax, int pmax, int part_threads) {
     ExactSmem s;
     s.us = umax | 1;
     s.hs = hmax | 1;
+    s.ps = (2 * hmax) | 1;
     s.tab = reinterpret_cast<double *>(raw);
     s.lgA = s.tab + (size_t)hmax * s.us;
     s.lgDA = s.lgA + hmax;
     s.fr = s.lgDA + (size_t)hmax * (pmax + 1);
     s.part = s.fr + hmax;
-    s.red = s.part + (size_t)part_threads * s.hs * 2;
+    s.red = s.part + (size_t)part_threads * s.ps;
     s.cwr = reinterpret_cast<long long *>(s.red + 32);
     s.cnt = reinterpret_cast<int *>(s.cwr + (size_t)(hmax + 1) * (pmax + 1));
+    s.col = s.cnt + umax;
     return s;
 }
 
@@ -156,60 +159,95 @@ struct GenoR {
 
 struct ExactItem {
     int U, P, H;
-    bool unit_counts, has_prior, null_prior, has_freqs;
+    int nA, nB;        // read columns [0, nA): count 1; [nA, nB): count 2..MCHB_EXACT_POW_MAX; [nB, U): the rest
+    int n_factors;     // mantissa factors of the product form = sum of the counts of the columns below nB
+    bool checked;      // the table holds entries that are not positive normal numbers
+    bool has_prior, null_prior, has_freqs;
     double lg_left, p_log_h;
 };
 
-// sum_r count_r * log(sum_k t[g_k][r]) for one genotype (header, point 2)
+// per-read probability of a genotype: the reference's left fold over the slots (likelihood.py:60-66)
 template <int PM>
+__device__ __forceinline__ double exact_rp(const double *const (&row)[PM], int P, int r) {
+    double rp = row[0][r];
+#pragma unroll
+    for (int k = 1; k < PM; k++)
+        if (k < P) rp += row[k][r];
+    return rp;
+}
+
+// mantissa in [1, 2) of a positive normal double; its biased exponent is hi >> 20
+__device__ __forceinline__ double mantissa_of(double x, int hi) {
+    return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+}
+
+// sum_r count_r * log(sum_k t[g_k][r]) for one genotype (header, point 2).  The reads of the table
+// are grouped by count: columns [0, nA) have count 1, [nA, nB) counts 2..MCHB_EXACT_POW_MAX,
+// [nB, U) anything else; s.cnt holds the counts in column order.  CHECKED: table entries may be
+// zero / denormal, so every rp is tested and an odd one sends the genotype to the reference's form.
+template <int PM, bool CHECKED>
 __device__ __forceinline__ double exact_llk(const GenoR<PM> &g, const ExactSmem &s, const ExactItem &it) {
     const double *row[PM];
 #pragma unroll
     for (int k = 0; k < PM; k++) row[k] = s.tab + (size_t)g.g[k] * s.us;
     double mant = 1.0, slow = 0.0;
-    int expo = 0, n_fast = 0, n_norm = 0;
-    bool odd = false;  // some rp is zero, denormal, negative, inf or NaN
+    int expo = 0;
+    unsigned worst = 0;  // max over reads of (hi - 0x00100000) as unsigned: >= 0x7fe00000 iff some rp is odd
+    // ---- count 1: one factor per read, renormalised every 512 reads
+    for (int base = 0; base < it.nA; base += 512) {
+        const int stop = min(it.nA, base + 512);
 #pragma unroll 4
-    for (int r = 0; r < it.U; r++) {
-        double rp = row[0][r];
-#pragma unroll
-        for (int k = 1; k < PM; k++)
-            if (k < it.P) rp += row[k][r];
-        const int hi = __double2hiint(rp);
-        odd = odd || (hi < 0x00100000) || (hi >= 0x7ff00000);
-        const int c = it.unit_counts ? 1 : s.cnt[r];  // uniform over the CTA
-        if (c >= 1 && c <= MCHB_EXACT_POW_MAX) {
-            // rp^c: c factors of the mantissa, c times the exponent
-            const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(rp));
-            expo += (hi >> 20) * c;
-            n_fast += c;
-            mant *= m;
-#pragma unroll 1
-            for (int q = 1; q < c; q++) mant *= m;
-            if (n_fast - n_norm >= 512) {  // keep the mantissa product far from overflow
-                const int mh = __double2hiint(mant);
-                expo += (mh >> 20) - 1023;
-                mant = __hiloint2double((mh & 0x000fffff) | 0x3ff00000, __double2loint(mant));
-                n_norm = n_fast;
-            }
-        } else {
-            slow += log(rp) * (double)c;
+        for (int r = base; r < stop; r++) {
+            const double rp = exact_rp<PM>(row, it.P, r);
+            const int hi = __double2hiint(rp);
+            if (CHECKED) worst = max(worst, (unsigned)(hi - 0x00100000));
+            expo += hi >> 20;
+            mant *= mantissa_of(rp, hi);
         }
+        const int mh = __double2hiint(mant);
+        expo += (mh >> 20) - 1023;
+        mant = mantissa_of(mant, mh);
     }
-    if (odd) {
-        // the reference's form, read by read (log(0) = -inf, NaN propagates)
-        double llk = 0.0;
-        for (int r = 0; r < it.U; r++) {
-            double rp = row[0][r];
-#pragma unroll
-            for (int k = 1; k < PM; k++)
-                if (k < it.P) rp += row[k][r];
-            llk += log(rp) * (it.unit_counts ? 1.0 : (double)s.cnt[r]);
+    // ---- small counts: count factors per read (uniform inner loop), renormalised every 32 reads
+    for (int base = it.nA; base < it.nB; base += 32) {
+        const int stop = min(it.nB, base + 32);
+#pragma unroll 1
+        for (int r = base; r < stop; r++) {
+            const double rp = exact_rp<PM>(row, it.P, r);
+            const int hi = __double2hiint(rp);
+            if (CHECKED) worst = max(worst, (unsigned)(hi - 0x00100000));
+            const int c = s.cnt[r];
+            const double m = mantissa_of(rp, hi);
+            expo += (hi >> 20) * c;
+#pragma unroll 1
+            for (int q = 0; q < c; q++) mant *= m;
         }
+        const int mh = __double2hiint(mant);
+        expo += (mh >> 20) - 1023;
+        mant = mantissa_of(mant, mh);
+    }
+    // ---- everything else in the reference's form
+#pragma unroll 1
+    for (int r = it.nB; r < it.U; r++) {
+        const double rp = exact_rp<PM>(row, it.P, r);
+        if (CHECKED) worst = max(worst, (unsigned)(__double2hiint(rp) - 0x00100000));
+        slow += log(rp) * (double)s.cnt[r];
+    }
+    if (CHECKED && worst >= 0x7fe00000u) {
+        // some rp is zero, denormal, negative, inf or NaN: read by read (log(0) = -inf, NaN propagates)
+        double llk = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < it.U; r++) llk += log(exact_rp<PM>(row, it.P, r)) * (double)s.cnt[r];
         return llk;
     }
-    const double e = (double)(expo - 1023 * n_fast);
+    const double e = (double)(expo - 1023 * it.n_factors);
     return (e * MCHB_LN2_HI + (e * MCHB_LN2_LO + log(mant))) + slow;
+}
+
+// log joint of a genotype; the table of almost every item is free of zeros (CHECKED = false)
+template <int PM>
+__device__ __forceinline__ double exact_llk_any(const GenoR<PM> &g, const ExactSmem &s, const ExactItem &it) {
+    return it.checked ? exact_llk<PM, true>(g, s, it) : exact_llk<PM, false>(g, s, it);
 }
 
 // calling/prior.py:116-179 for a sorted genotype: the dosage of an allele is the length of its run
@@ -309,6 +347,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
     ModeRec *red_m = reinterpret_cast<ModeRec *>(s.red + 8);  // [4]
     __shared__ int s_item;
     __shared__ int s_tabHP;  // (H << 8) | P the binomial table was filled for
+    __shared__ int s_groups[3];
     double *scratch = RECOMP ? nullptr : a.scratch + (size_t)blockIdx.x * a.scratch_stride;
     if (tid == 0) s_tabHP = -1;
 
@@ -334,7 +373,33 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
         it.has_freqs = freqs != nullptr;
         it.p_log_h = dP * log((double)H);
 
-        // ---- 1. table t[h][r] (likelihood.py:48-60 per haplotype), counts, binomials, prior tables
+        // ---- 1. read columns grouped by count (thread 0; the order of the reads does not matter to a
+        // product), table t[h][column] (likelihood.py:48-60 per haplotype), binomials, prior tables
+        if (tid == 0) {
+            int nA = 0, nB = 0, nf = 0;
+            for (int pass = 0; pass < 3; pass++) {
+                int col = pass == 0 ? 0 : (pass == 1 ? nA : nB);
+                for (int r = 0; r < U; r++) {
+                    const long long c = a.counts ? __ldg(a.counts + itd.counts_off + r) : 1;
+                    const int cls = c == 1 ? 0 : ((c >= 2 && c <= MCHB_EXACT_POW_MAX) ? 1 : 2);
+                    if (cls != pass) continue;
+                    s.col[r] = col;
+                    s.cnt[col] = (int)c;
+                    if (pass < 2) nf += (int)c;
+                    col++;
+                }
+                if (pass == 0) nA = col;
+                if (pass == 1) nB = col;
+            }
+            s_groups[0] = nA;
+            s_groups[1] = nB;
+            s_groups[2] = nf;
+        }
+        __syncthreads();
+        it.nA = s_groups[0];
+        it.nB = s_groups[1];
+        it.n_factors = s_groups[2];
+        int odd_entry = 0;
         for (int i = tid; i < U * H; i += nthr) {
             const int h = i / U, r = i - h * U;
             double prod = 1.0;
@@ -342,15 +407,11 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
                 double v = __ldg(R + ((size_t)r * N + j) * A + haps[h * N + j]);
                 if (!isnan(v)) prod *= v;
             }
-            s.tab[h * s.us + r] = prod / dP;
+            const double t = prod / dP;
+            s.tab[h * s.us + s.col[r]] = t;
+            odd_entry |= (unsigned)(__double2hiint(t) - 0x00100000) >= 0x7fe00000u;
         }
-        int not_unit = 0;
-        for (int r = tid; r < U; r += nthr) {
-            const long long c = a.counts ? __ldg(a.counts + itd.counts_off + r) : 1;
-            s.cnt[r] = (int)c;
-            not_unit |= (c != 1);
-        }
-        it.unit_counts = !__syncthreads_or(not_unit);
+        it.checked = __syncthreads_or(odd_entry) != 0;
         if (s_tabHP != ((H << 8) | P)) {  // uniform: read before the barrier inside the fill
             exact_fill_cwr(s.cwr, H, P, cstride, tid, nthr);
             if (tid == 0) s_tabHP = (H << 8) | P;
@@ -371,7 +432,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
             GenoR<PM> g;
             g.unrank(g0, P, s.cwr, cstride, H);
             for (long long gi = g0; gi < g1; gi++) {
-                const double llk = exact_llk<PM>(g, s, it);
+                const double llk = exact_llk_any<PM>(g, s, it);
                 if (a.mode == 1) {
                     a.out_gl[itd.gl_off + gi] = (float)llk;
                 } else {
@@ -381,7 +442,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
                         best.llk = llk;
                         best.idx = gi;
                     }
-                    if (!RECOMP) scratch[gi] = ljoint;
+                    if (!RECOMP) scratch[(gi - g0) * nthr + tid] = ljoint;  // [step][thread]: coalesced
                 }
                 g.increment(P);
             }
@@ -420,7 +481,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
         const int pt = a.part_threads;
         double ssum = 0.0;
         if (tid < pt) {
-            double *row = s.part + (size_t)tid * s.hs * 2;
+            double *row = s.part + (size_t)tid * s.ps;
             for (int i = 0; i < 2 * H; i++) row[i] = 0.0;
             const long long chunk2 = (G + pt - 1) / pt;
             const long long b0 = (long long)tid * chunk2;
@@ -428,14 +489,19 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
             if (b0 < G) {
                 GenoR<PM> g;
                 g.unrank(b0, P, s.cwr, cstride, H);
+                long long owner = b0 / chunk, step = b0 - owner * chunk;  // where the first pass parked genotype b0
                 for (long long gi = b0; gi < b1; gi++) {
                     double lj;
-                    if (!RECOMP) lj = scratch[gi];
-                    else lj = exact_llk<PM>(g, s, it) + (it.has_prior ? exact_log_prior<PM>(g, s, it) : 0.0);
+                    if (!RECOMP) lj = scratch[step * nthr + owner];
+                    else lj = exact_llk_any<PM>(g, s, it) + (it.has_prior ? exact_log_prior<PM>(g, s, it) : 0.0);
                     const double p = exp(lj - top);
                     ssum += p;
                     exact_tally<PM>(g, P, p, row);
                     g.increment(P);
+                    if (++step == chunk) {
+                        step = 0;
+                        owner++;
+                    }
                 }
             }
         }
@@ -444,7 +510,7 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
         // ---- 5. outputs: allele statistics (partial rows added in thread order), mode, support
         for (int i = tid; i < 2 * H; i += nthr) {
             double acc = 0.0;
-            for (int t = 0; t < pt; t++) acc += s.part[(size_t)t * s.hs * 2 + i];
+            for (int t = 0; t < pt; t++) acc += s.part[(size_t)t * s.ps + i];
             const double v = acc / stot;
             if (i & 1) a.out_occur[itd.hap_out_off + (i >> 1)] = v;
             else a.out_freqs[itd.hap_out_off + (i >> 1)] = v / dP;
@@ -480,8 +546,11 @@ __global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ Exac
 #pragma unroll
                 for (int k = 0; k < PM; k++) t.g[k] = k < P ? merged[k] : 0;
                 double lj;
-                if (!RECOMP) lj = scratch[t.rank(P, s.cwr, cstride)];
-                else lj = exact_llk<PM>(t, s, it) + (it.has_prior ? exact_log_prior<PM>(t, s, it) : 0.0);
+                if (!RECOMP) {
+                    const long long rk = t.rank(P, s.cwr, cstride), owner = rk / chunk;
+                    lj = scratch[(rk - owner * chunk) * nthr + owner];
+                }
+                else lj = exact_llk_any<PM>(t, s, it) + (it.has_prior ? exact_log_prior<PM>(t, s, it) : 0.0);
                 support_ljoint = add_log_prob(support_ljoint, lj);
                 int i = rem - 1;
                 while (i >= 0 && idx[i] == ns - 1) i--;
@@ -538,10 +607,10 @@ __global__ void __launch_bounds__(128) posterior_kernel(const __grid_constant__ 
         const double *freqs = (a.freqs && itd.freqs_off >= 0) ? a.freqs + itd.freqs_off : nullptr;
         const double dP = (double)P;
         ExactItem it;
-        it.U = 0;
+        it.U = it.nA = it.nB = it.n_factors = 0;
         it.P = P;
         it.H = H;
-        it.unit_counts = true;
+        it.checked = false;
         it.has_prior = !isnan(itd.inbreeding);
         it.null_prior = !(it.has_prior && itd.inbreeding != 0.0);
         it.has_freqs = freqs != nullptr;
@@ -593,14 +662,14 @@ __global__ void __launch_bounds__(128) posterior_kernel(const __grid_constant__ 
         // exp(x - (top + log(stot))) evaluated as exp(x - top) / stot
         const int pt = a.part_threads;
         if (a.out_freqs && tid < pt) {
-            double *row = s.part + (size_t)tid * s.hs * 2;
+            double *row = s.part + (size_t)tid * s.ps;
             for (int i = 0; i < 2 * H; i++) row[i] = 0.0;
         }
         for (long long gi = g0; gi < g1; gi++) gp[gi] = gp[gi] / stot;
         __syncthreads();
         if (a.out_freqs) {
             if (tid < pt) {
-                double *row = s.part + (size_t)tid * s.hs * 2;
+                double *row = s.part + (size_t)tid * s.ps;
                 const long long chunk2 = (G + pt - 1) / pt;
                 const long long b0 = (long long)tid * chunk2;
                 const long long b1 = b0 + chunk2 < G ? b0 + chunk2 : G;
@@ -616,7 +685,7 @@ __global__ void __launch_bounds__(128) posterior_kernel(const __grid_constant__ 
             __syncthreads();
             for (int i = tid; i < 2 * H; i += nthr) {
                 double acc = 0.0;
-                for (int t = 0; t < pt; t++) acc += s.part[(size_t)t * s.hs * 2 + i];
+                for (int t = 0; t < pt; t++) acc += s.part[(size_t)t * s.ps + i];
                 if (i & 1) {
                     a.out_occur[itd.hap_out_off + (i >> 1)] = acc;
                 } else {

@@ -898,16 +898,18 @@ int check_call_items(mchb_handle *h, const mchb_call_item *items, int64_t n_item
 // threads of a CTA that own a partial row of allele statistics: as many as fit 32 KB
 int exact_part_threads(const CallGeom &g) {
     int pt = 128;
-    while (pt > 1 && (size_t)pt * (g.hmax | 1) * 16 > 32768) pt >>= 1;
+    while (pt > 1 && (size_t)pt * ((2 * g.hmax) | 1) * 8 > 32768) pt >>= 1;
     return pt;
 }
 
 // host mirror of exact_carve()
 size_t exact_smem(const CallGeom &g, int umax, int part_threads) {
     const size_t us = (size_t)(umax | 1), hs = (size_t)(g.hmax | 1);
-    size_t d = (size_t)g.hmax * us + g.hmax + (size_t)g.hmax * (g.pmax + 1) + g.hmax + (size_t)part_threads * hs * 2 + 32 +
+    const size_t ps = (size_t)((2 * g.hmax) | 1);
+    (void)hs;
+    size_t d = (size_t)g.hmax * us + g.hmax + (size_t)g.hmax * (g.pmax + 1) + g.hmax + (size_t)part_threads * ps + 32 +
                (size_t)(g.hmax + 1) * (g.pmax + 1);
-    return d * 8 + (size_t)umax * 4 + 64;
+    return d * 8 + (size_t)umax * 8 + 64;
 }
 
 // Instantiations of exact_kernel: ploidies 2, 4, 6, 8 have kernels specialised for batches in which
@@ -980,7 +982,7 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
     int ctas_per_sm = 1;
     // one ploidy for the whole batch -> specialised kernel; parked log joints need a row per CTA
     const int fixed_p = (g.pmin == g.pmax) ? g.pmax : 0;
-    const unsigned long long row_bytes = sizeof(double) * (unsigned long long)g.gmax;
+    const unsigned long long row_bytes = sizeof(double) * ((unsigned long long)g.gmax + 128);  // [ceil(G / 128)][128]
     unsigned long long budget = MCHB_EXACT_SCRATCH_BUDGET;
     if (const char *env = getenv("MCHB_EXACT_SCRATCH_BYTES")) budget = strtoull(env, nullptr, 10);  // tests: force the low-memory path
     const bool recomp = mode == 0 && row_bytes > budget;
@@ -1017,7 +1019,7 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
             void *scratch;
             if ((rc = ensure(h, S_SCRATCH, (size_t)row_bytes * (size_t)grid, &scratch))) return rc;
             a.scratch = (double *)scratch;
-            a.scratch_stride = g.gmax;
+            a.scratch_stride = (int64_t)(row_bytes / sizeof(double));
         }  // else: a.scratch stays null and the second pass evaluates the log joints again
         if ((rc = stage_out(h, mem, S_OUT_A, out_alleles, n_items * pstride, &dalleles))) return rc;
         if ((rc = stage_out(h, mem, S_OUT_S, out_stats, n_items * 4, &dstats))) return rc;

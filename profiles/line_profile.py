@@ -33,7 +33,9 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.split("\n")))
 hdr = rows[1]
 ci, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
-data = [r for r in rows[2:] if len(r) > ci]
+data = [r for r in rows[2:] if len(r) > ci and r[0] != "Address"]
+if len(data) > len(seq) and len(data) % len(seq) == 0:
+    data = data[: len(seq)]  # several launches of the kernel in the report: take the first
 assert len(data) == len(seq), (len(data), len(seq))
 agg, samp = collections.Counter(), collections.Counter()
 for key, r in zip(seq, data):
