@@ -81,6 +81,12 @@ int32_t mchb_last_host_chunks(const mchb_handle *h);
 void *mchb_stream(const mchb_handle *h);
 int mchb_sm_count(const mchb_handle *h);
 
+/* Page-locked host memory for the bulk arrays of MCHB_MEM_HOST calls (no reference counterpart: the
+ * reference never leaves the host).  Copies from / to such buffers run at the full PCIe rate and
+ * overlap with kernels; pageable buffers work too, through the driver's staging. */
+int mchb_host_alloc(mchb_handle *h, int64_t bytes, void **out);
+int mchb_host_free(mchb_handle *h, void *p);
+
 /* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
  * TFLOP/s from a register-resident DFMA loop; the roofline denominator for the FP64-SIMT-bound
  * MCMC kernels. */

@@ -195,7 +195,7 @@ SYMBOLS = [
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
     "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
     "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch", "mchb_encode_assemble_tally_batch",
-    "mchb_mec_batch",
+    "mchb_mec_batch", "mchb_host_alloc", "mchb_host_free",
 ]
 
 
@@ -295,5 +295,9 @@ def load():
         ]
         L.mchb_mec_batch.restype = C.c_int
         L.mchb_mec_batch.argtypes = [vp, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, C.c_int64]
+        L.mchb_host_alloc.restype = C.c_int
+        L.mchb_host_alloc.argtypes = [vp, C.c_int64, C.POINTER(vp)]
+        L.mchb_host_free.restype = C.c_int
+        L.mchb_host_free.argtypes = [vp, vp]
         _lib = L
         return _lib

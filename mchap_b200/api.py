@@ -119,6 +119,31 @@ class Device:
         self._check(self._lib.mchb_measure_fp64_peak(self._h, C.byref(out)))
         return out.value
 
+    # ------------------------------------------------------------------ pinned host buffers
+    def pinned_empty(self, shape, dtype=np.float64):
+        """Uninitialised numpy array in page-locked host memory (freed when the array and its views
+        are garbage collected).  Use it for the bulk arrays of host-buffer calls: transfers run at the
+        full PCIe rate."""
+        import weakref
+
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        ptr = C.c_void_p()
+        self._check(self._lib.mchb_host_alloc(self._h, n * dtype.itemsize, C.byref(ptr)))
+        buf = (C.c_char * max(n * dtype.itemsize, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+        lib, h, addr = self._lib, self._h, ptr.value
+        weakref.finalize(buf, lambda: lib.mchb_host_free(h, C.c_void_p(addr)))
+        return arr
+
+    def pinned_concatenate(self, arrays, dtype):
+        """np.concatenate(arrays, axis=None) written straight into a page-locked buffer."""
+        n = int(sum(a.size for a in arrays))
+        out = self.pinned_empty(n, dtype)
+        if arrays and n:
+            np.concatenate(arrays, axis=None, out=out)
+        return out
+
     # ------------------------------------------------------------------ RNG / ranking
     def mt19937_words(self, seed, n):
         """numba's MT19937 output stream after np.random.seed(seed) (jitutils.py:180-183)."""
@@ -355,7 +380,9 @@ def count_genotypes(n_haplotypes, ploidy):
 class CallBatch:
     """Packed inputs of a batch of call / call-exact items (host arrays + descriptors)."""
 
-    def __init__(self, reads_list, haplotypes_list, ploidy, counts_list=None, priors=None):
+    def __init__(self, reads_list, haplotypes_list, ploidy, counts_list=None, priors=None, device=None):
+        """device: when given, the flat reads / counts / haplotypes arrays are built in page-locked
+        memory of that Device (one copy less on the way to the GPU)."""
         n = len(reads_list)
         self.n = n
         ploidies = np.broadcast_to(np.asarray(ploidy, dtype=np.int64), (n,))
@@ -399,9 +426,14 @@ class CallBatch:
         items["ploidy"] = ploidies
         items["freqs_off"], items["inbreeding"] = foffs, inbs
         self.items = items
-        self.reads = np.concatenate(rs) if rs else np.zeros(0)
-        self.haps = np.concatenate(hs) if hs else np.zeros(0, dtype=np.int8)
-        self.counts = np.concatenate(cs) if use_counts else None
+        if device is not None and n:
+            self.reads = device.pinned_concatenate(rs, np.float64)
+            self.haps = device.pinned_concatenate(hs, np.int8)
+            self.counts = device.pinned_concatenate(cs, np.int64) if use_counts else None
+        else:
+            self.reads = np.concatenate(rs) if rs else np.zeros(0)
+            self.haps = np.concatenate(hs) if hs else np.zeros(0, dtype=np.int8)
+            self.counts = np.concatenate(cs) if use_counts else None
         self.freqs = np.concatenate(fs) if fs else None
         self.hap_total = int(H_.sum())
         self.gl_total = int(self.n_genotypes.sum())

@@ -74,7 +74,17 @@ struct AsmArgs {
 };
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
-enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC_MARGIN, SC_COUNT };
+enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC_ERR_MUT, SC_ERR_STR, SC_COUNT };
+
+// Float32 screening: a proposal is settled without an exact evaluation only when its screened
+// Metropolis-Hastings ratio is below log(t) by more than  temp * E + MCHB_SCREEN_SLACK,  where E
+// (SC_ERR_MUT / SC_ERR_STR, per item) bounds |screened llk - exact llk| — derivation in DESIGN.md
+// section 4 'Error bound of the float32 screening' — and the slack covers the float32 log of the
+// uniform (<= 3.2e-5), the float conversion of t and the double roundings of the exact path.
+#define MCHB_SCREEN_SLACK 1.0e-3
+// reads whose screened probability falls below this fraction of the current one make the sub-step
+// needy (the error bound is proportional to 1 / this)
+#define MCHB_SCREEN_MIN_RATIO 1.0e-4f
 
 // more needy sub-steps than this in one window: evaluate the window with the lane-parallel exact
 // loop instead of one exact evaluation per needy sub-step
@@ -758,12 +768,12 @@ struct AsmCtx {
                 lprop = LOG_INT[copies_n] - LOG_INT[copies_o];
                 // ---- tier 1: float32 screening.  The proposal's row is the cached row of haplotype
                 // h times R[j][new] / R[j][old] (exact in real arithmetic); with float32 roundings and
-                // __logf the log-likelihood stays within `margin` of the exact one.  The exact step
+                // __logf the log-likelihood stays within SC_ERR_MUT of the exact one.  The exact step
                 // accepts only if exp(min(0, mh)) reaches t = u (current allele 1) or t = 1 - u
                 // (current allele 0) — see the cumulative sums in base_step — so a sub-step whose
-                // screened mh is below log(t) - margin is certainly rejected and needs no exact
+                // screened mh is below log(t) - (temp * SC_ERR_MUT + slack) is certainly rejected and needs no exact
                 // evaluation; everything else ("needy") is decided exactly below.
-                float a32f = 0.f;  // float32 accumulation: rounding <= U * 2^-24 * |llk|, far inside the margin
+                float a32f = 0.f;  // float32 accumulation: its rounding is part of SC_ERR_MUT
                 bool sane = true;
                 {
                     // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.
@@ -778,7 +788,7 @@ struct AsmCtx {
                     for (int r = 0; r < U; r++) {
                         const float rc_r = rc[r];
                         const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
-                        sane = sane && (rp > 1e-4f * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
+                        sane = sane && (rp > MCHB_SCREEN_MIN_RATIO * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
                         a32f = fmaf(__logf(rp), cw[r], a32f);
                     }
                 }
@@ -791,7 +801,7 @@ struct AsmCtx {
             }
             const double mh32 = d32 * temp + lprop;
             const double t_acc = (cur == 1) ? u : 1.0 - u;
-            const bool hopeless = (mh32 < (double)__logf((float)t_acc) - sc()[SC_MARGIN]) &&
+            const bool hopeless = (mh32 < (double)__logf((float)t_acc) - (temp * sc()[SC_ERR_MUT] + MCHB_SCREEN_SLACK)) &&
                                   (u < 0.99999999999999911182);  // 1 - 2^-50: keep clear of the cs1 <= u corner
             const unsigned needy = __ballot_sync(MCHB_FULL, mine && !hopeless);
             if (PRIOR && memo_ok && needy != 0)
@@ -931,7 +941,7 @@ struct AsmCtx {
             u = ws.next_double();
             have_u = true;
             if (u > 0.0 && u < 0.99999999999999911182 &&
-                (double)ent->smax < (double)__logf((float)u) - sc()[SC_MARGIN]) {
+                (double)ent->smax < (double)__logf((float)u) - (temp * sc()[SC_ERR_STR] + MCHB_SCREEN_SLACK)) {
                 evals += n_opt;  // certainly "stay" (see the screening below)
                 return;
             }
@@ -971,7 +981,7 @@ struct AsmCtx {
         }
         // ---- float32 screening (all variable positions bi-allelic, <= 32 options): the step
         // stays put unless sum_i exp(min(0, mh_i)) / n exceeds u; with every screened mh_i below
-        // log(u) - margin that sum is below u / e^2, so "stay" is certain and no exact
+        // log(u) - (temp * SC_ERR_STR + slack) that sum is below u, so "stay" is certain and no exact
         // log-likelihood is needed (same error budget as in mutation_compound_step).  The largest
         // screened mh is a function of the state only and is kept in the memo.
         {
@@ -1039,7 +1049,8 @@ struct AsmCtx {
                 ent->n_options = n_options;
             }
             __syncwarp();
-            if (u > 0.0 && u < 0.99999999999999911182 && smax < (double)__logf((float)u) - sc()[SC_MARGIN]) {
+            if (u > 0.0 && u < 0.99999999999999911182 &&
+                smax < (double)__logf((float)u) - (temp * sc()[SC_ERR_STR] + MCHB_SCREEN_SLACK)) {
                 evals += n_options;
                 return;
             }
@@ -1398,7 +1409,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
         if (isnan(v)) Rt[i] = 1.0;
     }
     __syncwarp();
-    // ---- float32 screening tables: allele ratios of bi-allelic flips, counts, safety margin
+    // ---- float32 screening tables: allele ratios of bi-allelic flips, counts, error bounds
     {
         float *rat = reinterpret_cast<float *>(sm + a.o_rat);
         float *c32 = reinterpret_cast<float *>(sm + a.o_c32);
@@ -1415,7 +1426,20 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
             csum += cnt[r];
         }
         csum = warp_sum(csum);
-        if (lane == 0) scv[SC_MARGIN] = 2.0 + 2e-3 * csum;
+        if (lane == 0) {
+            // Bounds of |screened - exact| log-likelihood, u = 2^-24:
+            //  mutation: a read's screened probability fma(q32[h], rat - 1, rpc) has relative error
+            //    <= 1.001 u ((P + 2) rpc / rp + 4) with rpc / rp <= 1.5 / MCHB_SCREEN_MIN_RATIO under the
+            //    `sane` test, i.e. <= 9.0e-4 (P + 2); log(1 + e) <= 1.02 e; __logf errs by <= 3.2e-5 on
+            //    (1e-30, 1e30); the float32 fma accumulation over U reads by <= 4.3e-6 U per unit count;
+            //  structural: products and sums of positive float32 values, relative error
+            //    <= 1.001 u (2 N + P + 1); accumulation over CH chunks per lane.
+            const double umax_reads = (double)U;
+            //  both: float32 underflow of a term (<= 2^-126 against rp > 1e-30): 1.2e-8 per operation.
+            const double under = 1.2e-8 * (double)(N + P + 2);
+            scv[SC_ERR_MUT] = csum * (1.02 * ((double)(P + 2) * 9.0e-4) + 3.2e-5 + 4.3e-6 * umax_reads + under);
+            scv[SC_ERR_STR] = csum * (1.02 * 6.0e-8 * (double)(2 * N + P + 1) + 3.2e-5 + 4.3e-6 * (double)(CH + 1) + under);
+        }
         __syncwarp();
     }
     // ---- per-item prior constants

@@ -65,7 +65,7 @@ struct ExactArgs {
 struct ExactSmem {
     double *tab;      // [hmax][us]     read x haplotype table, haplotype-major
     double *lgA;      // [hmax]         lgamma(alpha_a)
-    double *lgDA;     // [hmax][pmax+1] lgamma(d + alpha_a)
+    double *lgDA;     // [hmax][pmax+1] Dirichlet-multinomial term of allele a at dosage d
     double *fr;       // [hmax]         prior allele frequencies (staged)
     double *part;     // [part_threads][hs][2] partial allele statistics
     double *red;      // [32]: [0..7] per-warp sums, [8..] per-warp mode records / maxima
@@ -262,7 +262,7 @@ __device__ __forceinline__ double exact_log_prior(const GenoR<PM> &g, const Exac
             const bool last = (k == it.P - 1) || (g.g[k + 1 < PM ? k + 1 : k] != g.g[k]);
             if (last) {
                 if (it.null_prior) acc += LGAMMA_INT[run + 1];
-                else acc += s.lgDA[g.g[k] * (it.P + 1) + run] - (LGAMMA_INT[run + 1] + s.lgA[g.g[k]]);
+                else acc += s.lgDA[g.g[k] * (it.P + 1) + run];  // num - denom of prior.py:170-176, tabulated per item
                 run = 1;
             } else {
                 run += 1;
@@ -289,8 +289,8 @@ __device__ __forceinline__ double exact_prior_tables(const ExactSmem &s, int H, 
     for (int i = tid; i < H * (P + 1); i += nthr) {
         const int al = i / (P + 1), d = i - al * (P + 1);
         const double alpha = freqs ? freqs[al] * scale : alpha_const;
-        if (d == 0) s.lgA[al] = lgamma(alpha);
-        else s.lgDA[al * (P + 1) + d] = lgamma((double)d + alpha);
+        // term of an allele with dosage d: lgamma(d + alpha) - (lgamma(d + 1) + lgamma(alpha))
+        if (d > 0) s.lgDA[al * (P + 1) + d] = lgamma((double)d + alpha) - (LGAMMA_INT[d + 1] + lgamma(alpha));
     }
     double sum_alphas = 0.0;
     if (freqs) for (int al = 0; al < H; al++) sum_alphas += freqs[al] * scale;
@@ -338,7 +338,7 @@ __device__ __forceinline__ void exact_tally(const GenoR<PM> &g, int P, double p,
 // PM: register slots of a genotype; FIXED: every item of the launch has ploidy == PM (the slot
 // loops carry no predicates); RECOMP: no parked log joints, the second pass evaluates them again.
 template <int PM, bool FIXED, bool RECOMP>
-__global__ void __launch_bounds__(128) exact_kernel(const __grid_constant__ ExactArgs a) {
+__global__ void __launch_bounds__(128, PM <= 8 ? 8 : 4) exact_kernel(const __grid_constant__ ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;

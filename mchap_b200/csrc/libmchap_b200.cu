@@ -210,6 +210,20 @@ int32_t mchb_last_host_chunks(const mchb_handle *h) { return h ? h->host_chunks 
 void *mchb_stream(const mchb_handle *h) { return h ? (void *)h->stream : nullptr; }
 int mchb_sm_count(const mchb_handle *h) { return h ? h->sm_count : 0; }
 
+int mchb_host_alloc(mchb_handle *h, int64_t bytes, void **out) {
+    if (!h || !out || bytes < 0) return MCHB_ERR_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    *out = nullptr;
+    CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
+    return MCHB_OK;
+}
+
+int mchb_host_free(mchb_handle *h, void *p) {
+    if (!h) return MCHB_ERR_ARGUMENT;
+    if (p) CK(cudaFreeHost(p));
+    return MCHB_OK;
+}
+
 // ------------------------------------------------------------------------------------- RNG
 static int fill_streams(mchb_handle *h, const std::vector<uint32_t> &seeds, int64_t len, uint32_t **words) {
     void *dseeds, *dwords;
@@ -861,6 +875,8 @@ struct CallGeom {
 int check_call_items(mchb_handle *h, const mchb_call_item *items, int64_t n_items, int64_t reads_len,
                      bool has_counts, int64_t counts_len, int64_t haps_len, bool has_freqs, int64_t freqs_len,
                      int64_t hap_out_len, int64_t gl_len, bool use_reads, CallGeom &g) {
+    int memo_h = -1, memo_p = -1;
+    long long memo_g = 0;
     for (int64_t i = 0; i < n_items; i++) {
         const mchb_call_item &it = items[i];
         bool bad = it.n_reads < 0 || it.n_pos < 0 || it.max_allele < 0 || it.ploidy < 1 || it.n_haps < 1 ||
@@ -875,11 +891,20 @@ int check_call_items(mchb_handle *h, const mchb_call_item *items, int64_t n_item
         if (!bad && hap_out_len >= 0) bad = it.hap_out_off < 0 || it.hap_out_off + it.n_haps > hap_out_len;
         long long G = 0;
         if (!bad) {
-            // C(H+P-1, P) with overflow guard (long double estimate first)
-            long double est = 1.0L;
-            for (int k = 1; k <= it.ploidy; k++) est = est * (long double)(it.n_haps + it.ploidy - k) / (long double)k;
-            if (est > 4.0e18L) bad = true;
-            else G = comb_exact((long long)it.n_haps + it.ploidy - 1, it.ploidy);
+            if (it.n_haps == memo_h && it.ploidy == memo_p) {
+                G = memo_g;  // batches repeat a few (H, P) pairs
+            } else {
+                // C(H+P-1, P) with overflow guard (long double estimate first)
+                long double est = 1.0L;
+                for (int k = 1; k <= it.ploidy; k++) est = est * (long double)(it.n_haps + it.ploidy - k) / (long double)k;
+                if (est > 4.0e18L) bad = true;
+                else {
+                    G = comb_exact((long long)it.n_haps + it.ploidy - 1, it.ploidy);
+                    memo_h = it.n_haps;
+                    memo_p = it.ploidy;
+                    memo_g = G;
+                }
+            }
         }
         if (!bad && gl_len >= 0) bad = it.gl_off < 0 || it.gl_off + G > gl_len;
         if (bad) {
@@ -980,6 +1005,8 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
     if ((rc = stage_in(h, mem, S_HAPS, haplotypes, haplotypes_len, &dhaps))) return rc;
     if ((rc = stage_in(h, mem, S_FREQS, freqs, freqs_len, &dfreqs))) return rc;
     int ctas_per_sm = 1;
+    int threads = 128;
+    if (const char *env = getenv("MCHB_EXACT_THREADS")) threads = std::max(32, std::min(128, atoi(env) & ~31));  // tuning aid
     // one ploidy for the whole batch -> specialised kernel; parked log joints need a row per CTA
     const int fixed_p = (g.pmin == g.pmax) ? g.pmax : 0;
     const unsigned long long row_bytes = sizeof(double) * ((unsigned long long)g.gmax + 128);  // [ceil(G / 128)][128]
@@ -988,7 +1015,7 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
     const bool recomp = mode == 0 && row_bytes > budget;
 #define EXACT_PREP(PM, FIXED, RECOMP)                                                                                   \
     CK(cudaFuncSetAttribute(exact_kernel<PM, FIXED, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exact_kernel<PM, FIXED, RECOMP>, 128, smem))
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, exact_kernel<PM, FIXED, RECOMP>, threads, smem))
     MCHB_EXACT_DISPATCH(fixed_p, recomp, EXACT_PREP);
 #undef EXACT_PREP
     if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -1008,7 +1035,7 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
     a.hmax = g.hmax;
     a.pmax = g.pmax;
     a.pstride = pstride;
-    a.part_threads = part_threads;
+    a.part_threads = std::min(part_threads, threads);
     int64_t *dalleles = nullptr;
     double *dstats = nullptr, *dfo = nullptr, *doc = nullptr;
     float *dgl = nullptr;
@@ -1034,7 +1061,7 @@ int run_exact(mchb_handle *h, int mem, int mode, const mchb_call_item *items, in
         a.out_gl = dgl;
     }
     CK(cudaEventRecord(h->ev0, h->stream));
-#define EXACT_LAUNCH(PM, FIXED, RECOMP) exact_kernel<PM, FIXED, RECOMP><<<(unsigned)grid, 128, smem, h->stream>>>(a)
+#define EXACT_LAUNCH(PM, FIXED, RECOMP) exact_kernel<PM, FIXED, RECOMP><<<(unsigned)grid, threads, smem, h->stream>>>(a)
     MCHB_EXACT_DISPATCH(fixed_p, recomp, EXACT_LAUNCH);
 #undef EXACT_LAUNCH
     CK(cudaGetLastError());

@@ -36,9 +36,15 @@ for n, P, H, N, depth, prior in shapes:
     dt = (time.perf_counter() - t0) / reps
     dev.genotype_likelihoods(cb)
     gl_ms = dev.last_kernel_ms
+    cbp = CallBatch(reads, list(panels), P, counts, None if prior is None else [prior] * n, device=dev)
+    dev.call_exact_mode(cbp)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev.call_exact_mode(cbp)
+    dtp = (time.perf_counter() - t0) / reps
     print(json.dumps({
         "shape": "P=%d H=%d N=%d depth=%d prior=%s" % (P, H, N, depth, prior), "items": n, "genotypes": G,
         "mean_unique_reads": float(np.diff(batch.offsets).mean()),
         "mode_kernel_ms": kms / reps, "mode_genotypes_per_s_kernel": n * G / (kms / reps * 1e-3),
-        "mode_genotypes_per_s_e2e": n * G / dt, "mode_call_ms": dt * 1e3, "pack_ms": t_pack * 1e3,
+        "mode_genotypes_per_s_e2e": n * G / dt, "mode_call_ms": dt * 1e3, "mode_call_ms_pinned": dtp * 1e3, "mode_genotypes_per_s_e2e_pinned": n * G / dtp, "pack_ms": t_pack * 1e3,
         "gl_kernel_ms": gl_ms, "gl_genotypes_per_s_kernel": n * G / (gl_ms * 1e-3)}), flush=True)

@@ -565,3 +565,123 @@ def test_assemble_screening_stress_vs_oracle(dev, oracle, ploidy, n_pos, depth, 
         close(out[i][1], ref["llks"])
         assert results["rng_words"][i] == ref["words"]
         assert results["llk_evals"][i] == ref["llk_evals"]
+
+
+def _adversarial_reads(kind, rng, n_items, ploidy, n_pos, depth):
+    """Bi-allelic items (the float32-screened fast path) whose read probabilities stress the
+    screening arithmetic; returns (reads, counts) lists in the reference's encoding."""
+    reads, counts = [], []
+    for _ in range(n_items):
+        haps = rng.integers(0, 2, size=(ploidy, n_pos))
+        haps[rng.integers(0, ploidy)] = haps[0]                       # a duplicated haplotype
+        src = rng.integers(0, ploidy, size=depth)
+        calls = haps[src].copy()
+        flip = rng.random(calls.shape) < 0.02
+        calls[flip] ^= 1
+        start = rng.integers(0, max(n_pos // 2, 1), size=depth)
+        width = rng.integers(max(n_pos // 2, 1), n_pos + 1, size=depth)
+        cols = np.arange(n_pos)[None, :]
+        gap = (cols < start[:, None]) | (cols >= (start + width)[:, None])
+        if kind == "phred":
+            # --use-base-phred-scores with --base-error-rate 0: p = 1 - 10^(-q/10), q = 2 .. 41
+            q = rng.integers(2, 42, size=calls.shape)
+            p = 1.0 - 10.0 ** (q / -10.0)
+            other = (1.0 - p) / 3.0
+        elif kind == "wide":
+            # probabilities anywhere in 1e-9 .. 1 on both alleles: ratios R_new / R_old from 1e-9 to 1e9
+            p = 10.0 ** rng.uniform(-9, 0, size=calls.shape)
+            other = 10.0 ** rng.uniform(-9, 0, size=calls.shape)
+        elif kind == "zeros":
+            # error-free calls: the other allele has probability exactly 0 (ratio 0 or inf); some
+            # reads are left uninformative so that the chain is not pinned to -inf everywhere
+            p = np.ones(calls.shape)
+            other = np.zeros(calls.shape)
+            soft = rng.random(calls.shape) < 0.6
+            p[soft], other[soft] = 0.9976, 0.0008
+        elif kind == "ratio_one":
+            # nearly uninformative reads: ratios within 1e-6 of one, screened differences ~ rounding
+            p = 0.5 + rng.uniform(-1e-6, 1e-6, size=calls.shape)
+            other = 0.5 + rng.uniform(-1e-6, 1e-6, size=calls.shape)
+        else:
+            p = np.full(calls.shape, 0.9976)
+            other = np.full(calls.shape, 0.0008)
+        r = np.empty(calls.shape + (2,))
+        r[..., 0] = np.where(calls == 0, p, other)
+        r[..., 1] = np.where(calls == 1, p, other)
+        r[gap] = np.nan
+        if kind == "counts":
+            # few distinct reads with counts up to 10^4
+            r = r[:12]
+            c = rng.integers(1, 10001, size=len(r))
+        else:
+            c = np.ones(len(r), dtype=np.int64)
+        reads.append(r)
+        counts.append(c.astype(np.int64))
+    return reads, counts
+
+
+@pytest.mark.parametrize("kind,ploidy,n_pos,depth,temps,inbreeding", [
+    ("phred", 4, 8, 30, (1.0,), None),
+    ("phred", 4, 8, 60, (0.3, 1.0), 0.1),        # more than 32 distinct reads: two-chunk kernel
+    ("wide", 4, 8, 24, (1.0,), None),
+    ("wide", 2, 12, 20, (0.05, 1.0), None),
+    ("zeros", 4, 6, 20, (1.0,), None),
+    ("zeros", 4, 6, 20, (0.01, 0.2, 1.0), 0.2),
+    ("ratio_one", 4, 8, 30, (1.0,), None),
+    ("counts", 4, 8, 30, (1.0,), None),
+    ("counts", 6, 6, 30, (0.01, 0.1, 0.5, 1.0), None),
+    ("plain", 8, 4, 30, (0.01, 1.0), None),       # coldest temperature allowed by the CLIs' docs
+])
+def test_assemble_screening_adversarial_vs_oracle(dev, oracle, kind, ploidy, n_pos, depth, temps, inbreeding):
+    """the float32 screening (bi-allelic fast path) must never change a decision on
+    inputs outside the CLI defaults: per-base phred probabilities, probabilities over nine decades,
+    zero-probability alleles, ratios next to one, counts up to 10^4, temperatures down to 0.01."""
+    from mchap_b200 import DenovoMCMC
+
+    seed = sum(map(ord, kind)) + ploidy + n_pos
+    rng = np.random.default_rng(seed)
+    n_items, steps = 24, 120
+    reads, counts = _adversarial_reads(kind, rng, n_items, ploidy, n_pos, depth)
+    model = DenovoMCMC(ploidy=ploidy, n_alleles=[2] * n_pos, inbreeding=inbreeding, steps=steps, chains=2,
+                       temperatures=temps, random_seed=seed)
+    out, results = model.fit_batch(reads, counts, return_results=True, raw=True, errors="return")
+    screened = 0
+    for i in range(n_items):
+        try:
+            ref = _oracle_fit(oracle, model, reads[i], counts[i], [2] * n_pos)
+        except Exception as e:  # the reference's own failure modes (NaN log-likelihood ...) must match too
+            assert isinstance(out[i], type(e)), "item %d: oracle raised %r, device gave %r" % (i, e, out[i])
+            continue
+        assert not isinstance(out[i], BaseException), "item %d: %r" % (i, out[i])
+        np.testing.assert_array_equal(out[i][0], ref["genotypes"], err_msg="item %d" % i)
+        close(out[i][1], ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+        assert results["llk_evals"][i] == ref["llk_evals"]
+        screened += 1
+    assert screened >= n_items // 2
+
+
+@pytest.mark.parametrize("step_type", ["Gibbs", "Metropolis-Hastings"])
+def test_calling_mcmc_replay_harness(dev, oracle, step_type):
+    """North-star replay bar for the calling sampler: device and oracle driven by the same arbitrary
+    pre-drawn 32-bit word stream (not an MT19937 stream) give identical traces and consume the same
+    number of words."""
+    from mchap_b200.calling import CallingMCMC
+    from mchap_b200.synth import synth_haplotype_panel
+
+    n_items, P, H = 6, 4, 12
+    batch, panels, _ = synth_haplotype_panel(n_items, H, 8, P, depth=30, seed=41)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    words = np.random.default_rng(2024).integers(0, 2 ** 32, size=200000, dtype=np.uint64).astype(np.uint32)
+    model = CallingMCMC(ploidy=P, haplotypes=panels[0], steps=150, chains=2, random_seed=1, step_type=step_type,
+                        prior=(0.1, None))
+    traces, results = model.fit_batch(reads, counts, haplotypes_list=list(panels), return_results=True,
+                                      replay_words=words)
+    for i in range(n_items):
+        ref = oracle.calling_fit(reads[i], counts[i], P, panels[i], prior=(0.1, None), steps=150, chains=2,
+                                 random_seed=1, step_type=step_type, replay_words=words)
+        np.testing.assert_array_equal(traces[i].genotypes, ref["genotypes"], err_msg="item %d" % i)
+        close(traces[i].llks, ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+        assert results["rng_words"][i] < len(words)
