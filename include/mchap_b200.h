@@ -87,6 +87,11 @@ int mchb_sm_count(const mchb_handle *h);
 int mchb_host_alloc(mchb_handle *h, int64_t bytes, void **out);
 int mchb_host_free(mchb_handle *h, void *p);
 
+/* Profiling aid (no reference counterpart): per-temperature cycle / event counters of the assemble
+ * kernel, [8 temperatures][16 counters], filled only by a library built with -DMCHB_PROFILE
+ * (profiles/phase_profile.py); the product build returns MCHB_ERR_ARGUMENT. */
+int mchb_debug_counters(mchb_handle *h, uint64_t *out, int32_t n, int32_t reset);
+
 /* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
  * TFLOP/s from a register-resident DFMA loop; the roofline denominator for the FP64-SIMT-bound
  * MCMC kernels. */

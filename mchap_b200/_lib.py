@@ -195,7 +195,7 @@ SYMBOLS = [
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
     "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
     "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch", "mchb_encode_assemble_tally_batch",
-    "mchb_mec_batch", "mchb_host_alloc", "mchb_host_free",
+    "mchb_mec_batch", "mchb_host_alloc", "mchb_host_free", "mchb_debug_counters",
 ]
 
 
@@ -210,7 +210,9 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB_PATH
-        if _build.needs_build() and (_build.have_nvcc() or not os.path.exists(path)):
+        if os.environ.get("MCHB_LIB"):
+            path = os.environ["MCHB_LIB"]   # an explicitly chosen build (profiling counters)
+        elif _build.needs_build() and (_build.have_nvcc() or not os.path.exists(path)):
             _build.build()   # raises without nvcc: there is nothing else to run
         L = C.CDLL(path)
         vp = C.c_void_p
@@ -299,5 +301,7 @@ def load():
         L.mchb_host_alloc.argtypes = [vp, C.c_int64, C.POINTER(vp)]
         L.mchb_host_free.restype = C.c_int
         L.mchb_host_free.argtypes = [vp, vp]
+        L.mchb_debug_counters.restype = C.c_int
+        L.mchb_debug_counters.argtypes = [vp, vp, C.c_int32, C.c_int32]
         _lib = L
         return _lib

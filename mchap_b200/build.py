@@ -42,6 +42,21 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+PROFILE_LIB_PATH = os.path.join(LIB_DIR, "libmchap_b200_prof.so")
+
+
+def build_profile(force=False):
+    """The same library with -DMCHB_PROFILE (per-temperature cycle / event counters in the assemble
+    kernel); loaded instead of the product build when MCHB_LIB points at it (profiles/phase_profile.py)."""
+    if not force and os.path.exists(PROFILE_LIB_PATH) and \
+            all(os.path.getmtime(s) <= os.path.getmtime(PROFILE_LIB_PATH) for s in sources()):
+        return PROFILE_LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-DMCHB_PROFILE", "-o", PROFILE_LIB_PATH,
+                                                    os.path.join(CSRC, "libmchap_b200.cu")])
+    return PROFILE_LIB_PATH
+
+
 def build(force=False, verbose=False, extra_flags=()):
     if not force and not needs_build():
         return LIB_PATH

@@ -32,6 +32,22 @@
 
 namespace mchb {
 
+// Profiling build (-DMCHB_PROFILE, profiles/phase_profile.py): per-temperature cycle and event
+// counters of the assemble kernel, read back with mchb_debug_counters.  Absent from the product build.
+#ifdef MCHB_PROFILE
+__device__ unsigned long long g_asm_prof[8 * 16];
+#define MCHB_PROF_ADD(t, k, v)                                                                   \
+    do {                                                                                         \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_asm_prof[((t) & 7) * 16 + (k)], (unsigned long long)(v)); \
+    } while (0)
+#define MCHB_PROF_CLOCK() clock64()
+#else
+#define MCHB_PROF_ADD(t, k, v) do { (void)(v); } while (0)
+#define MCHB_PROF_CLOCK() 0ll
+#endif
+enum { PK_CYC_MUT = 0, PK_CYC_STR, PK_CYC_SLOT, PK_MUT_ACCEPT, PK_WINDOWS, PK_T2A_EVALS, PK_T2B_WINDOWS, PK_BASE_STEPS,
+       PK_STR_EXACT, PK_STR_SCREEN_STAY, PK_STR_MEMO_STAY, PK_INTERVALS, PK_CYC_SWAPSTEP, PK_STR_ACCEPT, PK_T2B_DONE };
+
 struct AsmArgs {
     const mchb_assemble_item *items;
     const int32_t *order;       // item ids handled by this launch
@@ -64,7 +80,7 @@ struct AsmArgs {
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
         o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache,
-        o_wmap, o_inv;
+        o_wmap, o_inv, o_hot;
     // tres = state slots resident in shared memory: tmax normally; 1 when the per-temperature
     // tables of a large shape would otherwise leave only one warp per SM — then the slot of the
     // temperature being stepped is swapped in from / out to slot_backing (global memory, L2)
@@ -290,7 +306,9 @@ __device__ __noinline__ void compute_row(const double *Rt_lane, double *row_lane
     for (int ch = 0; ch < CH; ch++) out[ch] = 1.0;
     const double *base = Rt_lane;
     const int pstride = g.A * UPAD;
-#pragma unroll 1
+    // (the kernels of the large shapes run one warp per scheduler: their loops are unrolled so that
+    // the shared-memory loads overlap; the one-chunk kernel is instruction-cache bound and is not)
+#pragma unroll(CH >= 2 ? 4 : 1)
     for (int j = 0; j < g.N; j++) {
         const double *p = base + ((uint32_t)k & g.amask) * UPAD;
         k >>= g.B;
@@ -315,7 +333,7 @@ __device__ __noinline__ double eval_rows(const double *q_lane, const double *cnt
 #pragma unroll
     for (int ch = 0; ch < CH; ch++) {
         double rp = 0.0;
-#pragma unroll 1
+#pragma unroll(CH >= 2 ? 4 : 1)
         for (int h = 0; h < P; h++) rp += q_lane[h * UPAD + ch * 32];
         acc += log(rp) * cnt_lane[ch * 32];
     }
@@ -366,6 +384,8 @@ struct AsmCtx {
     WordStream ws;
     int err;
     long long evals;
+    int prof_t = 0;  // index of the temperature being stepped
+    int n_acc;       // proposals accepted by the mutation compound step under way
 
     __device__ __forceinline__ AsmCtx(const AsmArgs &args, unsigned char *s, int l) : a(args), sm(s), lane(l) {}
 
@@ -462,7 +482,7 @@ struct AsmCtx {
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) {
             float rp = 0.f;
-#pragma unroll 1
+#pragma unroll(CH >= 2 ? 4 : 1)
             for (int hh = 0; hh < P; hh++) rp += qs[hh * UPAD + ch * 32];
             dst[ch * 32] = rp;
         }
@@ -561,6 +581,7 @@ struct AsmCtx {
     // lane-parallel path of mutation_compound_step instead.
     __device__ __forceinline__ void base_step(int s, int h, int j, int n_all, double temp, double &llk, const double u) {
         uint64_t *ks = keys(s);
+        MCHB_PROF_ADD(prof_t, PK_BASE_STEPS, 1);
         const uint64_t kh = ks[h];
         const int shift = B * j;
         const uint64_t clr = ~((uint64_t)amask << shift);
@@ -619,7 +640,11 @@ struct AsmCtx {
             err = MCHB_ITEM_CHOICE_RANGE;
             return;
         }
-        if (choice != cur) commit(s, h, (kh & clr) | ((uint64_t)choice << shift));
+        if (choice != cur) {
+            MCHB_PROF_ADD(prof_t, PK_MUT_ACCEPT, 1);
+            n_acc++;
+            commit(s, h, (kh & clr) | ((uint64_t)choice << shift));
+        }
         llk = ol[choice];
     }
 
@@ -631,8 +656,18 @@ struct AsmCtx {
     // walks the reads in read order like likelihood.py:45-68); the first accepting lane commits
     // and the sub-steps behind it are re-evaluated from the new state.  A sub-step at a position
     // with more than two alleles is a barrier handled by the serial base_step.
-    __device__ __forceinline__ void mutation_compound_step(int s, double temp, double &llk) {
+    // Per-temperature history that steers the choice between equivalent code paths (never the
+    // results): [4 t] accepted proposals of the previous mutation compound step at temperature t.
+    __device__ __forceinline__ int32_t *hot() const { return reinterpret_cast<int32_t *>(sm + a.o_hot); }
+
+    __device__ __forceinline__ void mutation_compound_step(int s, int t, double temp, double &llk) {
         const int n = P * N;
+        // A replica that accepted many proposals in its last compound step (a heated one, or a
+        // chain still far from a mode) gains nothing from screening whole windows of sub-steps from
+        // one state: every acceptance invalidates the window behind it.  Such steps decide their
+        // sub-steps one after the other, exactly, with no screening pass (tier 2a below).
+        const bool hot_mode = hot()[4 * t] * 4 >= n;
+        n_acc = 0;
         uint16_t *pm = perm();
         __syncwarp();
         if (n <= 32) {
@@ -724,7 +759,7 @@ struct AsmCtx {
         while (done < n && !err) {
             // screened quantities of this slot's sub-steps are still valid if the state is the
             // one they were computed for
-            const bool memo_ok = epoch()[a.tres + s] == epoch()[s];
+            const bool memo_ok = !hot_mode && epoch()[a.tres + s] == epoch()[s];
             const int i = done + lane;
             const bool active = i < n;
             const int hj = pm[active ? i : done];
@@ -745,6 +780,7 @@ struct AsmCtx {
                 continue;
             }
             const bool mine = lane < limit;
+            MCHB_PROF_ADD(prof_t, PK_WINDOWS, 1);
             const uint64_t kn = (kh & ~((uint64_t)amask << shift)) | ((uint64_t)(cur ^ 1) << shift);
             const double u = ws.double_at(2 * (mine ? lane : 0));
             double lprior_ratio, lprop, d32;
@@ -774,8 +810,8 @@ struct AsmCtx {
                 // screened mh is below log(t) - (temp * SC_ERR_MUT + slack) is certainly rejected and needs no exact
                 // evaluation; everything else ("needy") is decided exactly below.
                 float a32f = 0.f;  // float32 accumulation: its rounding is part of SC_ERR_MUT
-                bool sane = true;
-                {
+                bool sane = !hot_mode;
+                if (!hot_mode) {
                     // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.
                     // The subtraction hidden in it can lose relative accuracy when the proposal
                     // removes almost all of a read's probability, so reads with rp_new < 1e-4 rp_cur
@@ -794,7 +830,7 @@ struct AsmCtx {
                 }
                 const double a32 = (double)a32f;
                 d32 = sane ? (a32 - llk) + lprior_ratio : INFINITY;  // +inf: never screened out
-                if (mine) {
+                if (mine && !hot_mode) {
                     mc[0] = d32;
                     mc[1] = lprop;
                 }
@@ -806,7 +842,7 @@ struct AsmCtx {
             const unsigned needy = __ballot_sync(MCHB_FULL, mine && !hopeless);
             if (PRIOR && memo_ok && needy != 0)
                 lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
-            if (__popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
+            if (hot_mode || __popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
                 // ---- tier 2a: exact decisions for the needy sub-steps, in order (uniform code)
                 int completed = limit;
                 unsigned m = needy;
@@ -821,6 +857,7 @@ struct AsmCtx {
                     const double lrest = __shfl_sync(MCHB_FULL, lprior_ratio, l);
                     const double lpropl = __shfl_sync(MCHB_FULL, lprop, l);
                     install_row(s, hl, knl, 0);
+                    MCHB_PROF_ADD(prof_t, PK_T2A_EVALS, 1);
                     const double llk_x = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
                     const double mh = ((llk_x - llk) + lrest) * temp + lpropl;
                     const double la = np_minimum0(mh);
@@ -844,6 +881,8 @@ struct AsmCtx {
                         err = MCHB_ITEM_CHOICE_RANGE;
                     } else {
                         __syncwarp();
+                        MCHB_PROF_ADD(prof_t, PK_MUT_ACCEPT, 1);
+                        n_acc++;
                         ks[hl] = knl;  // the row is already installed
                         llk = llk_x;
                         refresh_rpc(s);
@@ -859,6 +898,7 @@ struct AsmCtx {
             // ---- tier 2b: many needy sub-steps: exact log-likelihood of every proposal of the
             // window, lane-parallel (reads in order, haplotypes in order)
             double llk_o = 0.0;
+            MCHB_PROF_ADD(prof_t, PK_T2B_WINDOWS, 1);
             {
                 const int astride = UPAD, pstride = A * UPAD;
 #pragma unroll 1
@@ -897,12 +937,16 @@ struct AsmCtx {
             const unsigned event = __ballot_sync(MCHB_FULL, mine && choice != cur);
             if (event == 0) {
                 // every evaluated proposal was rejected
+                MCHB_PROF_ADD(prof_t, PK_T2B_DONE, limit);
                 evals += limit;
                 ws.advance(2 * limit);
                 done += limit;
                 continue;
             }
             const int first = __ffs(event) - 1;
+            MCHB_PROF_ADD(prof_t, PK_T2B_DONE, first + 1);
+            MCHB_PROF_ADD(prof_t, PK_MUT_ACCEPT, 1);
+            n_acc++;
             evals += first + 1;
             ws.advance(2 * (first + 1));
             done += first + 1;
@@ -921,7 +965,10 @@ struct AsmCtx {
         }
         // every bi-allelic sub-step was screened from one and the same state: keep the memo
         __syncwarp();
-        if (!err && epoch()[s] == epoch_at_start && lane == 0) epoch()[a.tres + s] = epoch_at_start;
+        if (lane == 0) {
+            if (!err && !hot_mode && epoch()[s] == epoch_at_start) epoch()[a.tres + s] = epoch_at_start;
+            hot()[4 * t] = n_acc;
+        }
         __syncwarp();
     }
 
@@ -929,6 +976,7 @@ struct AsmCtx {
     __device__ __forceinline__ void interval_step(int s, int start, int stop, int step_type, double temp,
                                                   double &llk) {
         uint64_t *ks = keys(s);
+        MCHB_PROF_ADD(prof_t, PK_INTERVALS, 1);
         // ---- memo of this (type, interval) for the slot's current state
         const uint32_t ep = epoch()[s];
         const uint32_t skey = ((uint32_t)step_type << 16) | ((uint32_t)start << 8) | (uint32_t)stop;
@@ -943,6 +991,7 @@ struct AsmCtx {
             if (u > 0.0 && u < 0.99999999999999911182 &&
                 (double)ent->smax < (double)__logf((float)u) - (temp * sc()[SC_ERR_STR] + MCHB_SCREEN_SLACK)) {
                 evals += n_opt;  // certainly "stay" (see the screening below)
+                MCHB_PROF_ADD(prof_t, PK_STR_MEMO_STAY, 1);
                 return;
             }
         }
@@ -986,7 +1035,14 @@ struct AsmCtx {
         // screened mh is a function of the state only and is kept in the memo.
         {
             double smax = INFINITY;
-            if (B == 1 && n_options <= 32) {
+            // a replica whose last 16 screening passes all failed to prove "stay" (a heated one)
+            // skips the pass and probes again every 16th interval
+            int32_t *fails = hot() + 4 * prof_t + 1;
+            const int nf = *fails;
+            const bool try_screen = nf < 16 || (nf & 15) == 0;
+            __syncwarp();
+            if (lane == 0) *fails = nf + 1;
+            if (B == 1 && n_options <= 32 && try_screen) {
                 const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
                 const float *rt = rat() + lane;
                 const float *cw = c32() + lane;
@@ -1018,7 +1074,7 @@ struct AsmCtx {
 #pragma unroll
                     for (int ch = 0; ch < CH; ch++) {
                         float rp = 0.f;
-#pragma unroll 1
+#pragma unroll(CH >= 2 ? 4 : 1)
                         for (int hh = 0; hh < P; hh++) {
                             float v = qs[hh * UPAD + ch * 32];
                             v = (hh == h0) ? ra[ch] : v;
@@ -1052,6 +1108,9 @@ struct AsmCtx {
             if (u > 0.0 && u < 0.99999999999999911182 &&
                 smax < (double)__logf((float)u) - (temp * sc()[SC_ERR_STR] + MCHB_SCREEN_SLACK)) {
                 evals += n_options;
+                MCHB_PROF_ADD(prof_t, PK_STR_SCREEN_STAY, 1);
+                if (lane == 0) *fails = 0;
+                __syncwarp();
                 return;
             }
         }
@@ -1081,6 +1140,7 @@ struct AsmCtx {
                 install_row(s, h0, k0n, 0);
                 if (step_type == 0) install_row(s, h1, (k0 & mask_in) | (k1 & ~mask_in), 1);
                 const double llk_i = eval_llk(s);
+                MCHB_PROF_ADD(prof_t, PK_STR_EXACT, 1);
                 restore_row(s, h0, 0);
                 if (step_type == 0) restore_row(s, h1, 1);
                 double lprior_ratio = 0.0;
@@ -1132,6 +1192,7 @@ struct AsmCtx {
         __syncwarp();
         const int choice = searchsorted_right(op, n_options + 1, u);
         if (choice < n_options) {
+            MCHB_PROF_ADD(prof_t, PK_STR_ACCEPT, 1);
             const int h0 = o0[choice], h1 = o1[choice];
             const uint64_t k0 = ks[h0], k1 = ks[h1];
             const uint64_t k0n = (k1 & mask_in) | (k0 & ~mask_in);
@@ -1466,7 +1527,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
 }
 
 template <int CH, bool PRIOR>
-__global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const __grid_constant__ AsmArgs a) {
+__global__ void __launch_bounds__(128, CH == 1 ? MCHB_ASM_MINBLOCKS : (CH == 2 ? 2 : 1)) assemble_kernel(const __grid_constant__ AsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The launches of one call (rare shape classes first, the most populated class last) are
     // chained with programmatic dependent launch: the next kernel may start as soon as every CTA
@@ -1598,6 +1659,7 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
                 __syncwarp();
                 // ---- all temperatures start from the same state (mcmc.py:296-303)
                 c.slots = 0x76543210u;
+                for (int i = lane; i < 4 * T; i += 32) c.hot()[i] = 0;
                 // one resident slot, the others in the backing store (never in the CH = 1 kernels,
                 // whose hot loop stays free of the swap code)
                 const bool swap = CH >= 2 && a.tres < a.tmax && T > 1;
@@ -1643,14 +1705,23 @@ __global__ void __launch_bounds__(128, MCHB_ASM_MINBLOCKS) assemble_kernel(const
                             c.err = MCHB_ITEM_NAN_LLK;
                             break;
                         }
+                        c.prof_t = t;
+                        const long long pc0 = MCHB_PROF_CLOCK();
                         if (swap) {
                             slot_copy<CH>(a, c.sm, lane, s, false);
                             s = 0;
                         }
-                        c.mutation_compound_step(s, temp, llk);
+                        const long long pc1 = MCHB_PROF_CLOCK();
+                        c.mutation_compound_step(s, t, temp, llk);
+                        const long long pc2 = MCHB_PROF_CLOCK();
                         if (c.err) break;
                         c.structural_substeps(s, temp, llk, brow, blen);
+                        const long long pc3 = MCHB_PROF_CLOCK();
                         if (swap) slot_copy<CH>(a, c.sm, lane, c.slot(t), true);
+                        const long long pc4 = MCHB_PROF_CLOCK();
+                        MCHB_PROF_ADD(t, PK_CYC_MUT, pc2 - pc1);
+                        MCHB_PROF_ADD(t, PK_CYC_STR, pc3 - pc2);
+                        MCHB_PROF_ADD(t, PK_CYC_SLOT, (pc1 - pc0) + (pc4 - pc3));
                         if (c.err) break;
                         if (t > 0) c.chain_swap_step(t, temp, temps[t - 1], llk);
                         __syncwarp();

@@ -254,6 +254,28 @@ int mchb_mt19937_words(mchb_handle *h, int mem, uint32_t seed, uint32_t *out, in
     return MCHB_OK;
 }
 
+// ------------------------------------------------------------------- profiling-build counters
+int mchb_debug_counters(mchb_handle *h, uint64_t *out, int32_t n, int32_t reset) {
+    if (!h || !out || n < 0) return MCHB_ERR_ARGUMENT;
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < n; i++) out[i] = 0;
+#ifdef MCHB_PROFILE
+    unsigned long long tmp[8 * 16];
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyFromSymbol(tmp, g_asm_prof, sizeof(tmp)));
+    for (int i = 0; i < n && i < 8 * 16; i++) out[i] = tmp[i];
+    if (reset) {
+        memset(tmp, 0, sizeof(tmp));
+        CK(cudaMemcpyToSymbol(g_asm_prof, tmp, sizeof(tmp)));
+    }
+    return MCHB_OK;
+#else
+    (void)reset;
+    h->err = "library built without -DMCHB_PROFILE";
+    return MCHB_ERR_ARGUMENT;
+#endif
+}
+
 // --------------------------------------------------------------------------- FP64 pipe probe
 int mchb_measure_fp64_peak(mchb_handle *h, double *out_tflops) {
     if (!h || !out_tflops) return MCHB_ERR_ARGUMENT;
@@ -415,6 +437,7 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     args.o_scache = take((size_t)tres * MCHB_SCACHE_N * sizeof(ScEntry), 8);
     args.o_wmap = take((size_t)g.pmax * g.nmax * 2, 2);
     args.o_inv = take(32 * 4, 4);
+    args.o_hot = take((size_t)g.tmax * 4 * 4, 4);
     return (off + 15) & ~(size_t)15;
 }
 
