@@ -29,6 +29,11 @@
 #ifndef MCHB_ASM_MINBLOCKS
 #define MCHB_ASM_MINBLOCKS 4
 #endif
+// Launch bounds per read-chunk count.  One and two chunks: 4 CTAs of 4 warps, 128 registers (16 warps
+// per SM; shared memory allows as many at the headline shape).  Three and four chunks: shared memory
+// leaves at most 8 warps per SM, 255 registers.  Eight chunks: one or two warps per SM.
+#define MCHB_ASM_MAXTHREADS(CH) 128
+#define MCHB_ASM_MINCTAS(CH) ((CH) <= 2 ? MCHB_ASM_MINBLOCKS : ((CH) <= 4 ? 2 : 1))
 
 namespace mchb {
 
@@ -87,7 +92,20 @@ struct AsmArgs {
     int32_t tres;
     int32_t slot_bytes;          // bytes of one slot in the backing store
     unsigned char *slot_backing; // [grid warps][tmax][slot_bytes], only if tres < tmax
+    // The transposed reads tensor Rt is the largest per-item table and the exact paths (row
+    // recomputation) are its only readers: the one-chunk kernels keep it in shared memory, the
+    // kernels of larger items in a per-warp region of global memory (L2 resident), which roughly
+    // halves their shared memory per warp and lets twice as many warps share an SM.
+    double *rt_backing;          // [grid warps][rt_stride], only if CH >= 2
+    int64_t rt_stride;
 };
+
+template <int CH>
+__device__ __forceinline__ double *asm_rt(const AsmArgs &a, unsigned char *sm) {
+    if (CH == 1) return reinterpret_cast<double *>(sm);
+    const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    return a.rt_backing + (size_t)warp_global * a.rt_stride;
+}
 
 // uniform per-item scalars parked in shared memory (sc[]) to keep them out of registers
 enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC_ERR_MUT, SC_ERR_STR, SC_COUNT };
@@ -106,8 +124,11 @@ enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC
 // loop instead of one exact evaluation per needy sub-step
 #define MCHB_EXACT_SERIAL_MAX 8
 
-// entries of the per-slot memo of screened structural steps (direct mapped)
-#define MCHB_SCACHE_N 128
+// entries of the per-slot memo of screened structural steps (direct mapped): 128 in the one-chunk
+// kernels; 32 in the kernels of the large shapes, where shared memory decides how many warps an
+// SM holds (configs[3]: 58.4 -> 56.1 KB per warp, four warps per SM instead of three)
+#define MCHB_SCACHE_LOG2(CH) ((CH) == 1 ? 7 : 5)
+#define MCHB_SCACHE_N(CH) (1 << MCHB_SCACHE_LOG2(CH))
 struct ScEntry {
     uint32_t epoch;     // state epoch of the slot when the entry was filled
     uint32_t key;       // (type, start, stop)
@@ -306,9 +327,9 @@ __device__ __noinline__ void compute_row(const double *Rt_lane, double *row_lane
     for (int ch = 0; ch < CH; ch++) out[ch] = 1.0;
     const double *base = Rt_lane;
     const int pstride = g.A * UPAD;
-    // (the kernels of the large shapes run one warp per scheduler: their loops are unrolled so that
+    // (the kernels of three and more read chunks run one warp per scheduler: their loops are unrolled so that
     // the shared-memory loads overlap; the one-chunk kernel is instruction-cache bound and is not)
-#pragma unroll(CH >= 2 ? 4 : 1)
+#pragma unroll(CH >= 3 ? 4 : 1)
     for (int j = 0; j < g.N; j++) {
         const double *p = base + ((uint32_t)k & g.amask) * UPAD;
         k >>= g.B;
@@ -333,7 +354,7 @@ __device__ __noinline__ double eval_rows(const double *q_lane, const double *cnt
 #pragma unroll
     for (int ch = 0; ch < CH; ch++) {
         double rp = 0.0;
-#pragma unroll(CH >= 2 ? 4 : 1)
+#pragma unroll(CH >= 3 ? 4 : 1)
         for (int h = 0; h < P; h++) rp += q_lane[h * UPAD + ch * 32];
         acc += log(rp) * cnt_lane[ch * 32];
     }
@@ -349,7 +370,7 @@ __device__ __noinline__ void slot_copy(const AsmArgs &a, unsigned char *sm, int 
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char *back = a.slot_backing + ((size_t)warp_global * a.tmax + slot) * a.slot_bytes;
     const int32_t offs[7] = {a.o_q, a.o_mcache, a.o_key, a.o_scache, a.o_q32, a.o_rpc, a.o_epoch};
-    const int32_t lens[7] = {a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, MCHB_SCACHE_N * (int)sizeof(ScEntry),
+    const int32_t lens[7] = {a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, MCHB_SCACHE_N(CH) * (int)sizeof(ScEntry),
                              a.pmax * UPAD * 4, UPAD * 4, 8};
     __syncwarp();
     size_t boff = 0;
@@ -389,7 +410,7 @@ struct AsmCtx {
 
     __device__ __forceinline__ AsmCtx(const AsmArgs &args, unsigned char *s, int l) : a(args), sm(s), lane(l) {}
 
-    __device__ __forceinline__ double *Rt() const { return reinterpret_cast<double *>(sm); }
+    __device__ __forceinline__ double *Rt() const { return asm_rt<CH>(a, sm); }
     __device__ __forceinline__ double *cnt() const { return reinterpret_cast<double *>(sm + a.o_cnt); }
     __device__ __forceinline__ double *q() const { return reinterpret_cast<double *>(sm + a.o_q); }
     __device__ __forceinline__ double *dist() const { return reinterpret_cast<double *>(sm + a.o_dist); }
@@ -463,7 +484,7 @@ struct AsmCtx {
         return reinterpret_cast<double *>(sm + a.o_mcache) + (size_t)s * 2 * a.pmax * a.nmax;
     }
     __device__ __forceinline__ ScEntry *scache(int s) const {
-        return reinterpret_cast<ScEntry *>(sm + a.o_scache) + (size_t)s * MCHB_SCACHE_N;
+        return reinterpret_cast<ScEntry *>(sm + a.o_scache) + (size_t)s * MCHB_SCACHE_N(CH);
     }
     __device__ __forceinline__ void bump_epoch(int s) {
         uint32_t *e = epoch();
@@ -482,7 +503,7 @@ struct AsmCtx {
 #pragma unroll
         for (int ch = 0; ch < CH; ch++) {
             float rp = 0.f;
-#pragma unroll(CH >= 2 ? 4 : 1)
+#pragma unroll(CH >= 3 ? 4 : 1)
             for (int hh = 0; hh < P; hh++) rp += qs[hh * UPAD + ch * 32];
             dst[ch * 32] = rp;
         }
@@ -980,7 +1001,7 @@ struct AsmCtx {
         // ---- memo of this (type, interval) for the slot's current state
         const uint32_t ep = epoch()[s];
         const uint32_t skey = ((uint32_t)step_type << 16) | ((uint32_t)start << 8) | (uint32_t)stop;
-        ScEntry *ent = scache(s) + ((skey * 2654435761u) >> 25);
+        ScEntry *ent = scache(s) + ((skey * 2654435761u) >> (32 - MCHB_SCACHE_LOG2(CH)));
         double u = 0.0;
         bool have_u = false;
         if (ent->epoch == ep && ent->key == skey && ent->temp == (float)temp) {
@@ -1074,7 +1095,7 @@ struct AsmCtx {
 #pragma unroll
                     for (int ch = 0; ch < CH; ch++) {
                         float rp = 0.f;
-#pragma unroll(CH >= 2 ? 4 : 1)
+#pragma unroll(CH >= 3 ? 4 : 1)
                         for (int hh = 0; hh < P; hh++) {
                             float v = qs[hh * UPAD + ch * 32];
                             v = (hh == h0) ? ra[ch] : v;
@@ -1312,7 +1333,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
     const bool has_inb = !isnan(inbreeding);
     const bool pow2 = (P & (P - 1)) == 0;
     const double invP = 1.0 / (double)P;
-    double *Rt = reinterpret_cast<double *>(sm);
+    double *Rt = asm_rt<CH>(a, sm);
     double *cnt = reinterpret_cast<double *>(sm + a.o_cnt);
     double *homlp = reinterpret_cast<double *>(sm + a.o_homlp);
     double *dist = reinterpret_cast<double *>(sm + a.o_dist);
@@ -1527,7 +1548,7 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
 }
 
 template <int CH, bool PRIOR>
-__global__ void __launch_bounds__(128, CH == 1 ? MCHB_ASM_MINBLOCKS : (CH == 2 ? 2 : 1)) assemble_kernel(const __grid_constant__ AsmArgs a) {
+__global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH)) assemble_kernel(const __grid_constant__ AsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // The launches of one call (rare shape classes first, the most populated class last) are
     // chained with programmatic dependent launch: the next kernel may start as soon as every CTA
@@ -1542,7 +1563,7 @@ __global__ void __launch_bounds__(128, CH == 1 ? MCHB_ASM_MINBLOCKS : (CH == 2 ?
         uint32_t *e = c.epoch();
         for (int i = lane; i < 2 * a.tres; i += 32) e[i] = i < a.tres ? 1u : 0u;
         ScEntry *sc0 = c.scache(0);
-        for (int i = lane; i < a.tres * MCHB_SCACHE_N; i += 32) sc0[i].epoch = 0u;
+        for (int i = lane; i < a.tres * MCHB_SCACHE_N(CH); i += 32) sc0[i].epoch = 0u;
         __syncwarp();
         if (CH >= 2 && a.tres < a.tmax) {
             // every slot of the backing store starts from the same empty memo state

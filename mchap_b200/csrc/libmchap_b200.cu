@@ -58,6 +58,7 @@ enum Slot {
     S_TITEMS, S_TGENO, S_TSTATES, S_TCOUNTS, S_TFIRST, S_TRESULTS,
     S_EITEMS, S_ECALLS, S_EPROBS, S_ENALL, S_EREADS, S_ECOUNTS, S_ERESULTS,
     S_BACKING0, S_BACKING1, S_BACKING2, S_BACKING3, S_BACKING4, S_BACKING5, S_BACKING6, S_BACKING7, S_BACKING8, S_BACKING9,
+    S_RTBACK0, S_RTBACK1, S_RTBACK2, S_RTBACK3, S_RTBACK4, S_RTBACK5, S_RTBACK6, S_RTBACK7, S_RTBACK8, S_RTBACK9,
     S_NSLOTS
 };
 
@@ -407,7 +408,8 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
         off += bytes;
         return (int32_t)o;
     };
-    take((size_t)g.nmax * g.amax * upad * 8, 16);                      // Rt at 0
+    // Rt at 0 in the one-chunk kernels; the kernels of larger items keep it in global memory (L2)
+    take(ch >= 2 ? 0 : (size_t)g.nmax * g.amax * upad * 8, 16);
     args.o_cnt = take(upad * 8, 8);
     args.o_q = take(((size_t)tres * g.pmax + 2) * upad * 8, 8);  // + 2 spare rows
     args.o_dist = take((size_t)g.nmax * g.amax * 8, 8);
@@ -434,7 +436,7 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     args.o_bcs = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_epoch = take((size_t)tres * 2 * 4, 8);
     args.o_mcache = take((size_t)tres * 2 * g.pmax * g.nmax * 8, 8);
-    args.o_scache = take((size_t)tres * MCHB_SCACHE_N * sizeof(ScEntry), 8);
+    args.o_scache = take((size_t)tres * MCHB_SCACHE_N(ch) * sizeof(ScEntry), 8);
     args.o_wmap = take((size_t)g.pmax * g.nmax * 2, 2);
     args.o_inv = take(32 * 4, 4);
     args.o_hot = take((size_t)g.tmax * 4 * 4, 4);
@@ -452,28 +454,29 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
         tres = 1;
         per_warp = asm_layout(g, CH, tres, args);
     }
-    // warps per CTA: the value (4, 3, 2, 1) that keeps most warps resident per SM
-    // (228 KB of shared memory per SM, 1 KB reserved per resident CTA)
-    int warps_per_cta = 0, best = 0;
-    if (per_warp * 4 <= (size_t)h->smem_optin) warps_per_cta = 4;  // the usual case
-    for (int w = 4; w >= 1 && warps_per_cta == 0; w--) {
+    // warps per CTA: the value that keeps most warps resident per SM (shared memory and registers
+    // both count: the occupancy query knows the kernel's register allocation); ties go to 4, then
+    // to the larger CTA
+    constexpr int max_warps = MCHB_ASM_MAXTHREADS(CH) / 32;
+    int warps_per_cta = 0, best = 0, ctas_per_sm = 0;
+    for (int w = max_warps; w >= 1; w--) {
         if (per_warp * w > (size_t)h->smem_optin) continue;
-        const int resident = (int)((size_t)(228 * 1024) / (per_warp * w + 1024)) * w;
-        if (resident > best) best = resident;
-    }
-    for (int w = 4; w >= 1 && warps_per_cta == 0; w--)
-        if (per_warp * w <= (size_t)h->smem_optin &&
-            (int)((size_t)(228 * 1024) / (per_warp * w + 1024)) * w == best)
+        CK(cudaFuncSetAttribute(assemble_kernel<CH, PRIOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * w)));
+        int blocks = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, assemble_kernel<CH, PRIOR>, w * 32, per_warp * w));
+        const int resident = blocks * w;
+        if (resident > best || (resident == best && w == 4)) {
+            best = resident;
             warps_per_cta = w;
-    if (warps_per_cta == 0) {
+            ctas_per_sm = blocks;
+        }
+    }
+    if (warps_per_cta == 0 || ctas_per_sm < 1) {
         h->err = "assemble item needs more shared memory than one CTA can have";
         return MCHB_ERR_ARGUMENT;
     }
     const size_t smem = per_warp * warps_per_cta;
     CK(cudaFuncSetAttribute(assemble_kernel<CH, PRIOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int ctas_per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, assemble_kernel<CH, PRIOR>, warps_per_cta * 32, smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
     long long want = ((long long)n_items_class + warps_per_cta - 1) / warps_per_cta;
     long long grid = std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
     if (grid < 1) grid = 1;
@@ -490,13 +493,23 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
         const size_t upad = (size_t)CH * 32;
         auto r8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
         const size_t slot_bytes = (r8(g.pmax * upad * 8) + r8((size_t)2 * g.pmax * g.nmax * 8) + r8((size_t)g.pmax * 8) +
-                                   r8(MCHB_SCACHE_N * sizeof(ScEntry)) + r8(g.pmax * upad * 4) + r8(upad * 4) + r8(8) + 15) &
+                                   r8(MCHB_SCACHE_N(CH) * sizeof(ScEntry)) + r8(g.pmax * upad * 4) + r8(upad * 4) + r8(8) + 15) &
                                   ~(size_t)15;
         void *back;
         int rc = ensure(h, backing_slot, slot_bytes * (size_t)g.tmax * (size_t)grid * warps_per_cta, &back);
         if (rc) return rc;
         args.slot_bytes = (int32_t)slot_bytes;
         args.slot_backing = (unsigned char *)back;
+    }
+    args.rt_backing = nullptr;
+    args.rt_stride = 0;
+    if (CH >= 2) {
+        const size_t rt_elems = (size_t)g.nmax * g.amax * CH * 32;
+        void *back;
+        int rc = ensure(h, backing_slot - S_BACKING0 + S_RTBACK0, rt_elems * 8 * (size_t)grid * warps_per_cta, &back);
+        if (rc) return rc;
+        args.rt_backing = (double *)back;
+        args.rt_stride = (int64_t)rt_elems;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

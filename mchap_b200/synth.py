@@ -73,6 +73,16 @@ def encode_calls(calls, n_alleles, max_allele, error_rate=PFEIFFER_ERROR):
     return out
 
 
+def fragments_for_depth(depth_at_snv, n_pos, min_window=None):
+    """Fragments per item that give a mean read depth of ``depth_at_snv`` per SNV under the window
+    model above (window length uniform in ceil(n_pos/2)..n_pos covers (lo + n_pos) / (2 n_pos) of the
+    positions on average): 53 fragments for depth 40 at 8 SNVs, 133 for depth 100 at 16 SNVs
+    ("each read covers a random contiguous window ... so depth-at-SNV is about
+    the stated depth")."""
+    lo = (int(n_pos) + 1) // 2 if min_window is None else int(min_window)
+    return int(round(float(depth_at_snv) * 2.0 * n_pos / (lo + n_pos)))
+
+
 def synth_items(n_items, ploidy=4, n_pos=8, depth=40, n_alleles=2, error_rate=PFEIFFER_ERROR,
                 seed=0, min_window=None, window=True):
     """Generate ``n_items`` items; see the module docstring for the model."""
