@@ -53,7 +53,7 @@ typedef struct mchb_handle mchb_handle;
 typedef struct {
     int32_t max_ploidy;          /* 16 */
     int32_t max_key_bits;        /* 64: n_het_positions * bits_per_allele must fit */
-    int32_t max_unique_reads;    /* 256 per item for the warp-resident MCMC kernels */
+    int32_t max_unique_reads;    /* 1024 per item for the warp-resident assemble kernels (subject to shared memory) */
     int32_t max_temperatures;    /* 8 */
     int32_t max_haplotypes;      /* 256 known haplotypes per locus for call / call-exact */
 } mchb_limits;
@@ -171,6 +171,11 @@ typedef struct {
     int32_t break_rows, break_stride;
     const double *temperatures; /* pool indexed by item.temps_off */
     int32_t temperatures_len;
+    /* != 0: every recorded step has its haplotypes sorted lexicographically (first position most
+     * significant), the form GenotypeMultiTrace.__post_init__ gives a trace (assemble/classes.py:265-278,
+     * encoding/integer/sequence.py:78-110); 0: the sampler's own row order (the order the reference's
+     * _denovo_assembler returns, assemble/mcmc.py:418-425) */
+    int32_t sort_haplotypes;
     /* replay harness: when replay_words != NULL every item reads this pre-drawn (tempered)
      * 32-bit stream from word 0 instead of MT19937(seed) (always HOST memory) */
     const uint32_t *replay_words;

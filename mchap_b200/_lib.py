@@ -163,6 +163,7 @@ class AssembleParams(C.Structure):
         ("break_stride", C.c_int32),
         ("temperatures", C.c_void_p),
         ("temperatures_len", C.c_int32),
+        ("sort_haplotypes", C.c_int32),
         ("replay_words", C.c_void_p),
         ("replay_len", C.c_int64),
         ("rng_words_hint", C.c_int64),

@@ -4,6 +4,7 @@ The single-item, reference-shaped entry points (``DenovoMCMC.fit`` ...) live in
 ``mchap_b200.assemble`` / ``mchap_b200.calling`` and call into this module.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -69,9 +70,14 @@ class Device:
             raise MchapB200Error("mchb_create failed with status %d" % rc)
         self._h = h
         self.device = int(device)
+        self._pin_lock = threading.Lock()
 
     def close(self):
         if getattr(self, "_h", None):
+            for size, blocks in self.__dict__.get("_pin_free", {}).items():
+                for addr in blocks:
+                    self._lib.mchb_host_free(self._h, C.c_void_p(addr))
+            self.__dict__["_pin_free"], self.__dict__["_pin_held"] = {}, 0
             self._lib.mchb_destroy(self._h)
             self._h = None
 
@@ -120,21 +126,59 @@ class Device:
         return out.value
 
     # ------------------------------------------------------------------ pinned host buffers
+    PIN_POOL_CAP = 24 << 30   # bytes of released page-locked blocks kept for reuse
+
+    @staticmethod
+    def _pin_class(nbytes):
+        """Size class of a page-locked block: next multiple of 1/8 of the power of two below it
+        (at most 12.5 % larger than asked), 64 KB at least."""
+        nbytes = max(int(nbytes), 1 << 16)
+        step = 1 << max(nbytes.bit_length() - 4, 12)
+        return -(-nbytes // step) * step
+
+    def _pin_release(self, addr, size):
+        with self._pin_lock:
+            pool = self.__dict__.setdefault("_pin_free", {})
+            held = self.__dict__.get("_pin_held", 0)
+            if self._h and held + size <= self.PIN_POOL_CAP:
+                pool.setdefault(size, []).append(addr)
+                self.__dict__["_pin_held"] = held + size
+                return
+        if self._h:
+            self._lib.mchb_host_free(self._h, C.c_void_p(addr))
+
     def pinned_empty(self, shape, dtype=np.float64):
-        """Uninitialised numpy array in page-locked host memory (freed when the array and its views
-        are garbage collected).  Use it for the bulk arrays of host-buffer calls: transfers run at the
-        full PCIe rate."""
+        """Uninitialised numpy array in page-locked host memory.  Use it for the bulk arrays of
+        host-buffer calls: transfers run at the full PCIe rate and overlap with kernels.  Page-locking
+        is slow (about 2.5 GB/s), so blocks are recycled: when the array and all its views are garbage
+        collected the block goes back to a pool of this Device and the next request of that size class
+        gets it at no cost."""
         import weakref
 
         dtype = np.dtype(dtype)
         n = int(np.prod(shape))
-        ptr = C.c_void_p()
-        self._check(self._lib.mchb_host_alloc(self._h, n * dtype.itemsize, C.byref(ptr)))
-        buf = (C.c_char * max(n * dtype.itemsize, 1)).from_address(ptr.value)
+        size = self._pin_class(n * dtype.itemsize)
+        addr = None
+        with self._pin_lock:
+            free = self.__dict__.setdefault("_pin_free", {}).get(size)
+            if free:
+                addr = free.pop()
+                self.__dict__["_pin_held"] -= size
+        if addr is None:
+            ptr = C.c_void_p()
+            self._check(self._lib.mchb_host_alloc(self._h, size, C.byref(ptr)))
+            addr = ptr.value
+        buf = (C.c_char * size).from_address(addr)
         arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
-        lib, h, addr = self._lib, self._h, ptr.value
-        weakref.finalize(buf, lambda: lib.mchb_host_free(h, C.c_void_p(addr)))
+        weakref.finalize(buf, self._pin_release, addr, size).atexit = False
         return arr
+
+    def trace_buffer(self, n, dtype):
+        """Output array of a batch call: page-locked (pooled) when it is large enough to matter."""
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        if nbytes >= (8 << 20):
+            return self.pinned_empty(int(n), dtype)
+        return np.empty(max(int(n), 1), dtype=dtype)
 
     def pinned_concatenate(self, arrays, dtype):
         """np.concatenate(arrays, axis=None) written straight into a page-locked buffer."""
@@ -277,8 +321,8 @@ class Device:
         per = chains * steps
         a_len = int(per * batch.items["ploidy"].astype(np.int64).sum())
         l_len = per * n
-        alleles = np.zeros(max(a_len, 1), dtype=np.int32)
-        llks = np.zeros(max(l_len, 1), dtype=np.float64)
+        alleles = self.trace_buffer(a_len, np.int32)
+        llks = self.trace_buffer(l_len, np.float64)
         results = np.zeros(n, dtype=ITEM_RESULT_DTYPE)
         p = L.CallMcmcParams()
         p.steps, p.chains, p.step_type = int(steps), int(chains), int(step_type)
@@ -441,7 +485,8 @@ class CallBatch:
 
 
 def make_assemble_params(steps, chains, fix_homozygous, p_recombination, p_partial_dosage, p_dosage,
-                         break_table, break_len, temperatures, replay_words=None, rng_words_hint=0):
+                         break_table, break_len, temperatures, replay_words=None, rng_words_hint=0,
+                         sort_haplotypes=False):
     """Build the parameter struct; returns (params, keepalive tuple of the arrays it points to)."""
     bt = np.ascontiguousarray(break_table, dtype=np.float64)
     bl = np.ascontiguousarray(break_len, dtype=np.int32)
@@ -460,6 +505,7 @@ def make_assemble_params(steps, chains, fix_homozygous, p_recombination, p_parti
     p.break_stride = bt.shape[1]
     p.temperatures = tp.ctypes.data
     p.temperatures_len = tp.size
+    p.sort_haplotypes = 1 if sort_haplotypes else 0
     p.replay_words = None if rw is None else rw.ctypes.data
     p.replay_len = 0 if rw is None else rw.size
     p.rng_words_hint = int(rng_words_hint)

@@ -15,8 +15,8 @@ Batch conventions shared by every ``*_batch`` method:
   list instead, so one bad item does not discard the finished results of the others.
 
 Limits of the CUDA kernels (``mchb_get_limits``; items outside them get ``NotImplementedError``, never
-an approximation): ploidy <= 16, variable positions x bits per allele <= 64, <= 256 distinct reads
-per item, <= 8 temperatures.
+an approximation): ploidy <= 16, variable positions x bits per allele <= 64, <= 1024 distinct reads
+per item (and tables that fit one CTA's shared memory), <= 8 temperatures.
 """
 import ctypes as C
 from dataclasses import dataclass
@@ -236,12 +236,13 @@ class DenovoMCMC(object):
                     lens=(reads.size, 0 if counts is None else counts.size, nall.size,
                           0 if initial is None else initial.size))
 
-    def _params(self, nmax, replay_words=None, temperatures=None):
+    def _params(self, nmax, replay_words=None, temperatures=None, sort_haplotypes=False):
         table, lens = break_table(nmax, self.alpha, self.beta, self.n_intervals)
         return make_assemble_params(
             self.steps, self.chains, self.fix_homozygous, self.recombination_step_probability,
             self.partial_dosage_step_probability, self.dosage_step_probability, table, lens,
-            self._temperatures() if temperatures is None else temperatures, replay_words=replay_words)
+            self._temperatures() if temperatures is None else temperatures, replay_words=replay_words,
+            sort_haplotypes=sort_haplotypes)
 
     # ------------------------------------------------------------------ full traces
     def fit_batch(self, reads_list, counts_list=None, initial_list=None, n_alleles_list=None,
@@ -249,32 +250,44 @@ class DenovoMCMC(object):
                   inbreeding_list=None, temperatures_list=None, errors="raise"):
         """Run ``fit`` for many items in one device call.
 
-        raw=True returns unsorted (genotypes, llks) arrays instead of GenotypeMultiTrace;
-        the other keywords are described in the module docstring."""
+        raw=True returns the sampler's own (genotypes, llks) arrays (haplotypes in the order the
+        chain holds them, as the reference's _denovo_assembler returns them) instead of
+        GenotypeMultiTrace objects, whose steps have their haplotypes sorted — on the device, while
+        the step is recorded.  The returned arrays are views of one page-locked batch buffer (recycled
+        by the Device once every trace of the batch is garbage collected); the other keywords are
+        described in the module docstring."""
         assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(reads_list)
         pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds, ploidy_list, inbreeding_list,
                         temperatures_list)
         items, go, lo = pk["items"], pk["genotypes_len"], pk["llks_len"]
-        out_g = np.zeros(max(go, 1), dtype=np.int8)
-        out_l = np.full(max(lo, 1), np.nan, dtype=np.float64)
-        params, keep = self._params(pk["nmax"], replay_words, pk["temperatures"])
+        out_g = dev.trace_buffer(go, np.int8)
+        out_l = dev.trace_buffer(lo, np.float64)
+        params, keep = self._params(pk["nmax"], replay_words, pk["temperatures"], sort_haplotypes=not raw)
         results = dev.assemble_call(
             items, params, pk["reads"], pk["counts"], pk["n_alleles"], pk["initial"], out_g, out_l,
             pk["lens"] + (go, lo))
         out = [None] * n
         cs = self.chains * self.steps
+        status = results["status"]
+        bad = np.flatnonzero(status != 0)
+        for i in bad:
+            _settle(out, int(i), status[i], n, errors)
+        ok = status == 0
+        N_, P_ = items["n_pos"].tolist(), items["ploidy"].tolist()
+        g0_, l0_ = items["genotypes_off"].tolist(), items["llks_off"].tolist()
+        wrap = (lambda g, l: (g, l)) if raw else GenotypeMultiTrace._presorted
+        chains, steps = self.chains, self.steps
         for i in range(n):
-            if not _settle(out, i, results["status"][i], n, errors):
+            if not ok[i]:
                 continue
-            N, P = int(items["n_pos"][i]), int(items["ploidy"][i])
-            g0, l0 = int(items["genotypes_off"][i]), int(items["llks_off"][i])
-            g = out_g[g0: g0 + cs * P * N].reshape(self.chains, self.steps, P, N)
-            l = out_l[l0: l0 + cs].reshape(self.chains, self.steps)
+            N, P, g0, l0 = N_[i], P_[i], g0_[i], l0_[i]
+            g = out_g[g0: g0 + cs * P * N].reshape(chains, steps, P, N)
+            l = out_l[l0: l0 + cs].reshape(chains, steps)
             if N == 0:
                 l[:] = np.nan  # no variable position: nothing was sampled (mcmc.py:188-199)
-            out[i] = (g, l) if raw else GenotypeMultiTrace(g, l)
+            out[i] = wrap(g, l)
         if return_results:
             return out, results
         return out
@@ -293,27 +306,31 @@ class DenovoMCMC(object):
             t["chains"], t["steps"], t["burn"], t["max_unique"] = self.chains, self.steps, burn, table
             t["states_off"] = _excl(pn * table)
             t["tallies_off"] = np.arange(len(idx), dtype=np.int64) * table * self.chains
-            return (t, np.zeros(max(int((pn * table).sum()), 1), dtype=np.int8),
-                    np.zeros(max(len(idx) * table * self.chains, 1), dtype=np.int32),
-                    np.zeros(max(len(idx) * table * self.chains, 1), dtype=np.int32))
+            return (t, np.empty(max(int((pn * table).sum()), 1), dtype=np.int8),
+                    np.empty(max(len(idx) * table * self.chains, 1), dtype=np.int32),
+                    np.empty(max(len(idx) * table * self.chains, 1), dtype=np.int32))
 
         def collect(idx, t, tres, states, counts, first):
             over = []
-            for k, i in enumerate(idx):
-                if isinstance(out[i], BaseException):
+            counts, first = counts.astype(np.int64), first.astype(np.int64)   # once, not per item
+            st, nu = tres["status"].tolist(), tres["n_het"].tolist()
+            P_, N_ = items["ploidy"][idx].tolist(), items["n_pos"][idx].tolist()
+            so_, to_ = t["states_off"].tolist(), t["tallies_off"].tolist()
+            C_ = self.chains
+            for k, i in enumerate(np.asarray(idx).tolist()):
+                if st[k] != 0:
+                    if isinstance(out[i], BaseException):
+                        continue
+                    if st[k] == TALLY_OVERFLOW:
+                        over.append(i)
+                    else:
+                        _settle(out, i, st[k], n, errors)
                     continue
-                if int(tres["status"][k]) == TALLY_OVERFLOW:
-                    over.append(i)
+                if out[i] is not None and isinstance(out[i], BaseException):
                     continue
-                if not _settle(out, i, tres["status"][k], n, errors):
-                    continue
-                u = int(tres["n_het"][k])
-                P, N = int(items["ploidy"][i]), int(items["n_pos"][i])
-                so, to = int(t["states_off"][k]), int(t["tallies_off"][k])
-                out[i] = TraceTally(
-                    states[so: so + u * P * N].reshape(u, P, N).copy(),
-                    counts[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64),
-                    first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64))
+                u, P, N, so, to = nu[k], P_[k], N_[k], so_[k], to_[k]
+                out[i] = TraceTally(states[so: so + u * P * N].reshape(u, P, N),
+                                    counts[to: to + u * C_].reshape(u, C_), first[to: to + u * C_].reshape(u, C_))
             return over
 
         return tally_items, collect

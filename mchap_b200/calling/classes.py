@@ -305,27 +305,29 @@ class CallingMCMC(object):
                 np.cumsum(table * P_[:-1], out=so[1:])
             t["states_off"] = so
             t["tallies_off"] = np.arange(len(sel), dtype=np.int64) * table * self.chains
-            return (t, np.zeros(max(int((table * P_).sum()), 1), dtype=np.int32),
-                    np.zeros(max(len(sel) * table * self.chains, 1), dtype=np.int32),
-                    np.zeros(max(len(sel) * table * self.chains, 1), dtype=np.int32))
+            return (t, np.empty(max(int((table * P_).sum()), 1), dtype=np.int32),
+                    np.empty(max(len(sel) * table * self.chains, 1), dtype=np.int32),
+                    np.empty(max(len(sel) * table * self.chains, 1), dtype=np.int32))
 
         def collect(sel, t, tres, states, counts, first):
             over = []
-            for k, i in enumerate(sel):
+            counts, first = counts.astype(np.int64), first.astype(np.int64)   # once, not per item
+            st, nu = tres["status"].tolist(), tres["n_het"].tolist()
+            so_, to_ = t["states_off"].tolist(), t["tallies_off"].tolist()
+            P_ = ploidy[np.asarray(sel, dtype=np.int64)].tolist()
+            C_ = self.chains
+            for k, i in enumerate(np.asarray(sel).tolist()):
                 if isinstance(out[i], BaseException):
                     continue
-                if int(tres["status"][k]) == L.ITEM_TALLY_OVERFLOW:
-                    over.append(i)
+                if st[k] != 0:
+                    if st[k] == L.ITEM_TALLY_OVERFLOW:
+                        over.append(i)
+                    else:
+                        settle(i, st[k])
                     continue
-                if not settle(i, tres["status"][k]):
-                    continue
-                u = int(tres["n_het"][k])
-                P = int(ploidy[i])
-                so, to = int(t["states_off"][k]), int(t["tallies_off"][k])
-                out[i] = AllelesTraceTally(
-                    states[so: so + u * P].reshape(u, P).copy(),
-                    counts[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64),
-                    first[to: to + u * self.chains].reshape(u, self.chains).astype(np.int64), len(haps[i]))
+                u, P, so, to = nu[k], P_[k], so_[k], to_[k]
+                out[i] = AllelesTraceTally(states[so: so + u * P].reshape(u, P), counts[to: to + u * C_].reshape(u, C_),
+                                           first[to: to + u * C_].reshape(u, C_), len(haps[i]))
             return over
 
         table = max(1, min(int(max_unique), max(kept, 1)))

@@ -85,7 +85,8 @@ struct AsmArgs {
     // byte offsets of the per-warp arrays (host computed, asm_layout()); Rt is at offset 0
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
         o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache,
-        o_wmap, o_inv, o_hot;
+        o_wmap, o_inv, o_hot, o_hmap, o_rank;
+    int32_t sort_recorded;       // record every step with its haplotypes sorted (assemble/classes.py:265-278)
     // tres = state slots resident in shared memory: tmax normally; 1 when the per-temperature
     // tables of a large shape would otherwise leave only one warp per SM — then the slot of the
     // temperature being stepped is swapped in from / out to slot_backing (global memory, L2)
@@ -1620,7 +1621,11 @@ __global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH))
             {
                 const uint8_t *fixa = c.fixa();
                 __syncwarp();
-                for (int i = lane; i < step_sz; i += 32) wmap[i] = (uint16_t)fixa[i % Nf];
+                uint16_t *hmap = reinterpret_cast<uint16_t *>(c.sm + a.o_hmap);
+                for (int i = lane; i < step_sz; i += 32) {
+                    wmap[i] = (uint16_t)fixa[i % Nf];
+                    hmap[i] = (uint16_t)(((i / Nf) << 8) | (i % Nf));  // (haplotype, position) of byte i
+                }
                 __syncwarp();
                 for (int i = lane; i < P * N; i += 32) {
                     const int h = i / N, k = i - h * N;
@@ -1754,11 +1759,44 @@ __global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH))
                         const uint64_t *ks = c.slot_keys(c.slot(T - 1));
                         int8_t *dst = ogc + (size_t)step * step_sz;
                         __syncwarp();
+                        if (a.sort_recorded) {
+                            // GenotypeMultiTrace keeps every step with its haplotypes sorted
+                            // lexicographically, first position most significant (assemble/classes.py:
+                            // 265-278 -> encoding/integer/sequence.py:78-110).  Fixed positions are equal
+                            // in all haplotypes, so the packed keys decide: lane h ranks its key
+                            // (ties keep their order), and the rows are written at their ranks.
+                            uint8_t *rk = c.sm + a.o_rank;
+                            const uint16_t *hmap = reinterpret_cast<const uint16_t *>(c.sm + a.o_hmap);
+                            if (lane < P) {
+                                const uint64_t km = ks[lane];
+                                int r = 0;
 #pragma unroll 1
-                        for (int i = lane; i < step_sz; i += 32) {
-                            const uint32_t m = wmap[i];
-                            const uint32_t v = (uint32_t)(ks[(m >> 8) & 0x7f] >> (m & 63)) & c.amask;
-                            dst[i] = (int8_t)((m & 0x8000u) ? v : m);
+                                for (int k = 0; k < P; k++) {
+                                    const uint64_t kk = ks[k];
+                                    const uint64_t d = kk ^ km;
+                                    bool less = k < lane;  // equal keys
+                                    if (d != 0) {
+                                        const int sh = ((__ffsll((long long)d) - 1) / c.B) * c.B;  // first differing position
+                                        less = ((uint32_t)(kk >> sh) & c.amask) < ((uint32_t)(km >> sh) & c.amask);
+                                    }
+                                    r += less ? 1 : 0;
+                                }
+                                rk[lane] = (uint8_t)r;
+                            }
+                            __syncwarp();
+#pragma unroll 1
+                            for (int i = lane; i < step_sz; i += 32) {
+                                const uint32_t m = wmap[i], hp = hmap[i];
+                                const uint32_t v = (uint32_t)(ks[(m >> 8) & 0x7f] >> (m & 63)) & c.amask;
+                                dst[(int)rk[hp >> 8] * Nf + (int)(hp & 255u)] = (int8_t)((m & 0x8000u) ? v : m);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int i = lane; i < step_sz; i += 32) {
+                                const uint32_t m = wmap[i];
+                                const uint32_t v = (uint32_t)(ks[(m >> 8) & 0x7f] >> (m & 63)) & c.amask;
+                                dst[i] = (int8_t)((m & 0x8000u) ? v : m);
+                            }
                         }
                         if (lane == 0) olc[step] = llk;
                         __syncwarp();

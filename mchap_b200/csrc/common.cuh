@@ -14,6 +14,7 @@
 
 #define MCHB_MAX_PLOIDY 16
 #define MCHB_MAX_TEMPS 8
+#define MCHB_MAX_READS 1024  // distinct reads per assemble item (read chunks of 32: 1, 2, 3, 4, 8, 16, 32 per lane)
 #define MCHB_FULL 0xffffffffu
 
 namespace mchb {

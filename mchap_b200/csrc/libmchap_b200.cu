@@ -57,8 +57,8 @@ enum Slot {
     S_HAPS, S_FREQS, S_SCRATCH, S_INIT32, S_OUT_A32, S_OUT_A, S_OUT_S, S_OUT_F, S_OUT_O, S_OUT_C, S_OUT_GL, S_OUT_GP, S_LLKS, S_CHUNKS,
     S_TITEMS, S_TGENO, S_TSTATES, S_TCOUNTS, S_TFIRST, S_TRESULTS,
     S_EITEMS, S_ECALLS, S_EPROBS, S_ENALL, S_EREADS, S_ECOUNTS, S_ERESULTS,
-    S_BACKING0, S_BACKING1, S_BACKING2, S_BACKING3, S_BACKING4, S_BACKING5, S_BACKING6, S_BACKING7, S_BACKING8, S_BACKING9,
-    S_RTBACK0, S_RTBACK1, S_RTBACK2, S_RTBACK3, S_RTBACK4, S_RTBACK5, S_RTBACK6, S_RTBACK7, S_RTBACK8, S_RTBACK9,
+    S_BACKING0, S_BACKING1, S_BACKING2, S_BACKING3, S_BACKING4, S_BACKING5, S_BACKING6, S_BACKING7, S_BACKING8, S_BACKING9, S_BACKING10, S_BACKING11, S_BACKING12, S_BACKING13,
+    S_RTBACK0, S_RTBACK1, S_RTBACK2, S_RTBACK3, S_RTBACK4, S_RTBACK5, S_RTBACK6, S_RTBACK7, S_RTBACK8, S_RTBACK9, S_RTBACK10, S_RTBACK11, S_RTBACK12, S_RTBACK13,
     S_NSLOTS
 };
 
@@ -200,7 +200,7 @@ void mchb_get_limits(mchb_limits *out) {
     if (!out) return;
     out->max_ploidy = MCHB_MAX_PLOIDY;
     out->max_key_bits = 64;
-    out->max_unique_reads = 256;
+    out->max_unique_reads = MCHB_MAX_READS;
     out->max_temperatures = MCHB_MAX_TEMPS;
     out->max_haplotypes = 256;
 }
@@ -440,6 +440,8 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     args.o_wmap = take((size_t)g.pmax * g.nmax * 2, 2);
     args.o_inv = take(32 * 4, 4);
     args.o_hot = take((size_t)g.tmax * 4 * 4, 4);
+    args.o_hmap = take((size_t)g.pmax * g.nmax * 2, 2);
+    args.o_rank = take(16, 1);
     return (off + 15) & ~(size_t)15;
 }
 
@@ -551,9 +553,10 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         h->err = "bad assemble parameters";
         return MCHB_ERR_ARGUMENT;
     }
-    constexpr int NCLS = 10;
+    constexpr int NCLS = 14;
+    static const int CLS_CH[7] = {1, 2, 3, 4, 8, 16, 32};
     // ---- validate, classify by unique-read chunk count and prior use, collect seeds
-    std::vector<int32_t> order[NCLS];  // class = 2 * (index of CH in {1, 2, 3, 4, 8}) + has_prior
+    std::vector<int32_t> order[NCLS];  // class = 2 * (index of CH in {1, 2, 3, 4, 8, 16, 32}) + has_prior
     AsmGeom geom[NCLS];
     std::map<uint32_t, int32_t> seed_index;
     std::vector<uint32_t> seeds;
@@ -580,7 +583,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         results[i].n_het = 0;
         results[i].rng_words = 0;
         results[i].llk_evals = 0;
-        if (it.n_reads > 256 || it.ploidy > MCHB_MAX_PLOIDY || it.n_temps > MCHB_MAX_TEMPS || it.n_pos > 255 ||
+        if (it.n_reads > MCHB_MAX_READS || it.ploidy > MCHB_MAX_PLOIDY || it.n_temps > MCHB_MAX_TEMPS || it.n_pos > 255 ||
             it.max_allele > 255) {
             results[i].status = MCHB_ITEM_UNSUPPORTED;
             continue;
@@ -588,8 +591,26 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
         if (it.n_pos == 0) {  // nothing to sample: empty traces, NaN llks are written by the host shim
             continue;
         }
-        int cls = 2 * (it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 96 ? 2 : it.n_reads <= 128 ? 3 : 4) +
-                  (std::isnan(it.inbreeding) ? 0 : 1);
+        const int chi = it.n_reads <= 32 ? 0 : it.n_reads <= 64 ? 1 : it.n_reads <= 96 ? 2 : it.n_reads <= 128 ? 3 :
+                        it.n_reads <= 256 ? 4 : it.n_reads <= 512 ? 5 : 6;
+        {
+            // an item whose own tables exceed one CTA's shared memory is reported as unsupported
+            // (per item: it must not take the rest of the batch with it)
+            AsmGeom gi;
+            gi.nmax = it.n_pos;
+            gi.amax = it.max_allele;
+            gi.pmax = it.ploidy;
+            gi.tmax = it.n_temps;
+            gi.maxopt = std::max({gi.pmax * (gi.pmax - 1), gi.amax, (int)pp.break_stride, 2});
+            AsmArgs tmp;
+            size_t pw = asm_layout(gi, CLS_CH[chi], gi.tmax, tmp);
+            if (pw > (size_t)h->smem_optin && gi.tmax > 1 && CLS_CH[chi] >= 2) pw = asm_layout(gi, CLS_CH[chi], 1, tmp);
+            if (pw > (size_t)h->smem_optin) {
+                results[i].status = MCHB_ITEM_UNSUPPORTED;
+                continue;
+            }
+        }
+        int cls = 2 * chi + (std::isnan(it.inbreeding) ? 0 : 1);
         order[cls].push_back((int32_t)i);
         AsmGeom &g = geom[cls];
         g.nmax = std::max(g.nmax, it.n_pos);
@@ -611,6 +632,17 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
     for (int c = 0; c < NCLS; c++) {
         AsmGeom &g = geom[c];
         g.maxopt = std::max({g.pmax * (g.pmax - 1), g.amax, (int)pp.break_stride, 2});
+        // a class is launched with the largest dimensions of its items: if that combination does not
+        // fit one CTA (each item alone does), the class is run item by item is not worth the code for
+        // a case this rare — its items are reported as unsupported instead of failing the call
+        if (order[c].empty()) continue;
+        AsmArgs tmp;
+        size_t pw = asm_layout(g, CLS_CH[c / 2], g.tmax, tmp);
+        if (pw > (size_t)h->smem_optin && g.tmax > 1 && CLS_CH[c / 2] >= 2) pw = asm_layout(g, CLS_CH[c / 2], 1, tmp);
+        if (pw > (size_t)h->smem_optin) {
+            for (int32_t id : order[c]) results[id].status = MCHB_ITEM_UNSUPPORTED;
+            order[c].clear();
+        }
     }
     // ---- device copies of the small tables
     void *ditems, *dstream, *dbreaks, *dbreaklen, *dtemps, *dcounter, *dresults;
@@ -772,6 +804,7 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                 args.stream_len = pp.replay_words ? pp.replay_len : stream_len;
                 args.steps = pp.steps;
                 args.chains = pp.chains;
+                args.sort_recorded = pp.sort_haplotypes;
                 args.fix_homozygous = pp.fix_homozygous;
                 args.p_recomb = pp.p_recombination;
                 args.p_partial = pp.p_partial_dosage;
@@ -801,7 +834,11 @@ int mchb_assemble_batch(mchb_handle *h, int mem, const mchb_assemble_params *par
                     case 6: rc = launch_assemble<4, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                     case 7: rc = launch_assemble<4, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                     case 8: rc = launch_assemble<8, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
-                    default: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 9: rc = launch_assemble<8, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 10: rc = launch_assemble<16, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 11: rc = launch_assemble<16, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    case 12: rc = launch_assemble<32, false>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
+                    default: rc = launch_assemble<32, true>(h, st, args, geom[c], n_c, chained, S_BACKING0 + c); break;
                 }
                 if (rc) return rc;
                 chained = true;

@@ -685,3 +685,65 @@ def test_calling_mcmc_replay_harness(dev, oracle, step_type):
         close(traces[i].llks, ref["llks"])
         assert results["rng_words"][i] == ref["words"]
         assert results["rng_words"][i] < len(words)
+
+
+@pytest.mark.parametrize("ploidy,n_pos,n_alleles,depth,temps", [
+    (4, 8, 2, 40, (1.0,)),
+    (6, 5, 4, 30, (0.2, 1.0)),     # two bits per allele, a heated replica
+    (8, 10, 3, 70, (1.0,)),        # three read chunks (Rt in global memory)
+    (2, 1, 2, 10, (1.0,)),
+])
+def test_fit_batch_sorts_haplotypes_on_the_device(dev, ploidy, n_pos, n_alleles, depth, temps):
+    """fit_batch returns GenotypeMultiTrace objects whose steps were sorted by the kernel while it
+    recorded them (mchb_assemble_params.sort_haplotypes): identical to the host-side lexsort of the
+    raw trace (reference: assemble/classes.py:265-278), fixed positions included."""
+    from mchap_b200 import DenovoMCMC
+    from mchap_b200.assemble.classes import sort_haplotypes
+    from mchap_b200.synth import synth_items
+
+    n_items = 12
+    batch = synth_items(n_items, ploidy=ploidy, n_pos=n_pos, depth=depth, n_alleles=n_alleles, seed=ploidy * n_pos)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    model = DenovoMCMC(ploidy=ploidy, n_alleles=[n_alleles] * n_pos, steps=200, chains=2, temperatures=temps,
+                       random_seed=9, fix_homozygous=0.9)
+    raw = model.fit_batch(reads, counts, raw=True)
+    traces = model.fit_batch(reads, counts)
+    changed = 0
+    for i in range(n_items):
+        want = sort_haplotypes(raw[i][0])
+        np.testing.assert_array_equal(traces[i].genotypes, want, err_msg="item %d" % i)
+        np.testing.assert_array_equal(traces[i].llks, raw[i][1])
+        changed += int((want != raw[i][0]).any())
+    assert changed > 0 or ploidy * n_pos <= 2
+
+
+@pytest.mark.parametrize("depth,ploidy,n_pos,temps,inbreeding", [
+    (300, 4, 8, (1.0,), None),        # 16 read chunks per lane
+    (700, 4, 6, (0.5, 1.0), 0.1),     # 32 read chunks, a heated replica, Dirichlet-multinomial prior
+    (1024, 2, 5, (1.0,), None),       # the limit
+])
+def test_assemble_hundreds_of_distinct_reads_vs_oracle(dev, oracle, depth, ploidy, n_pos, temps, inbreeding):
+    """reads encoded from base qualities are nearly all distinct, so items with far more
+    than 256 distinct reads are common in deep targeted data.  The 16- and 32-chunk kernels take up to
+    1024 distinct reads; trajectories stay bit-identical to the oracle."""
+    from mchap_b200 import DenovoMCMC
+
+    rng = np.random.default_rng(depth)
+    n_items, steps = 3, 60
+    reads, counts = _adversarial_reads("phred", rng, n_items, ploidy, n_pos, depth)
+    assert all(len(r) == depth for r in reads)
+    model = DenovoMCMC(ploidy=ploidy, n_alleles=[2] * n_pos, inbreeding=inbreeding, steps=steps, chains=2,
+                       temperatures=temps, random_seed=depth)
+    out, results = model.fit_batch(reads, counts, return_results=True, raw=True)
+    for i in range(n_items):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], [2] * n_pos)
+        np.testing.assert_array_equal(out[i][0], ref["genotypes"], err_msg="item %d" % i)
+        close(out[i][1], ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+        assert results["llk_evals"][i] == ref["llk_evals"]
+    # one read more than the limit: that item alone is refused
+    big = reads + [np.concatenate([reads[0], reads[0][:1]] * 2)[:1025] if depth == 1024 else reads[0]]
+    if depth == 1024:
+        res = model.fit_batch(big, [None] * 4, errors="return", raw=True)
+        assert isinstance(res[3], NotImplementedError) and not isinstance(res[0], BaseException)

@@ -96,3 +96,4 @@ def test_call_batch_layout():
         oo += H
         go += G
     assert (cb.hap_total, cb.gl_total, cb.pmax) == (oo, go, int(ploidy.max()))
+
