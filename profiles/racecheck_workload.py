@@ -24,6 +24,10 @@ if which in ("all", "assemble"):
     b = synth_items(2, ploidy=8, n_pos=16, depth=100, seed=3)  # resident-slot swap
     DenovoMCMC(ploidy=8, n_alleles=[2] * 16, steps=3, chains=1, temperatures=(0.01, 0.1, 0.5, 1.0),
                random_seed=3).fit_batch([b.item(i)[0] for i in range(2)], [b.item(i)[1] for i in range(2)])
+    rng = np.random.default_rng(9)   # 300 distinct reads: the 16-chunk kernel, Rt in global memory
+    r = np.stack([rng.random((300, 5)) * 0.5 + 0.5, np.zeros((300, 5))], axis=-1)
+    r[..., 1] = (1 - r[..., 0]) / 3
+    DenovoMCMC(ploidy=4, n_alleles=[2] * 5, steps=4, chains=1, temperatures=(0.05, 1.0), random_seed=4).fit_batch([r])
 if which in ("all", "assemble", "multiallelic"):
     rng = np.random.default_rng(5)
     reads, counts, nalls = [], [], []
