@@ -364,6 +364,8 @@ def config_call_mcmc(R, dev, args, peak_tf, cpu):
     R.barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
+        d2h = int(out["alleles"].nbytes + out["llks"].nbytes + out["results"].nbytes)
+        del out                         # the page-locked trace block goes back to the Device's pool
         out = dev.call_mcmc(cb, steps, chains, st, init, pmax)
         kms += dev.last_kernel_ms
         launches += dev.last_kernel_launches
@@ -379,7 +381,7 @@ def config_call_mcmc(R, dev, args, peak_tf, cpu):
         "value": R.world * n_steps * reps / (kms_max * 1e-3), "n_gpus": R.world, "ms_per_pass": kms_max / reps,
         "e2e": {"value": R.world * n_steps * reps / dt_max, "unit": UNIT,
                 "h2d_bytes_per_step": int(cb.reads.nbytes + cb.counts.nbytes + cb.haps.nbytes + cb.items.nbytes),
-                "d2h_bytes_per_step": int(out["alleles"].nbytes + out["llks"].nbytes + out["results"].nbytes),
+                "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * dt_max / reps},
         "gpu_launches": launches, "mean_unique_reads": float(batch.n_reads().mean()),
         "roofline": fp64_roofline(flops, kms * 1e-3, peak_tf, "call_mcmc_kernel", {

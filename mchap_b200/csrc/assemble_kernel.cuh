@@ -864,7 +864,9 @@ struct AsmCtx {
             const unsigned needy = __ballot_sync(MCHB_FULL, mine && !hopeless);
             if (PRIOR && memo_ok && needy != 0)
                 lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
-            if (hot_mode || __popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
+            // (the kernels of larger items always take the serial tier: their Rt lives in global memory
+            // and the lane-per-sub-step loop of tier 2b would read it with 32 different rows per load)
+            if (CH >= 2 || hot_mode || __popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
                 // ---- tier 2a: exact decisions for the needy sub-steps, in order (uniform code)
                 int completed = limit;
                 unsigned m = needy;

@@ -14,6 +14,8 @@ from mchap_b200 import DenovoMCMC  # noqa: E402
 from mchap_b200.synth import synth_items  # noqa: E402
 
 SHAPES = {
+    "cfg1d": dict(ploidy=4, n_pos=8, depth=53, temps=(1.0,)),          # depth 40 at every SNV
+    "cfg3d": dict(ploidy=8, n_pos=16, depth=133, temps=(0.01, 0.1, 0.5, 1.0)),
     "cfg1": dict(ploidy=4, n_pos=8, depth=40, temps=(1.0,)),
     "cfg3": dict(ploidy=8, n_pos=16, depth=100, temps=(0.01, 0.1, 0.5, 1.0)),
     "hex2": dict(ploidy=6, n_pos=8, depth=40, temps=(0.2, 1.0)),

@@ -29,6 +29,8 @@ NAMES = ["cyc_mutation", "cyc_structural", "cyc_slot_copy", "mut_accepts", "wind
 
 SHAPES = {
     "cfg3": dict(n_items=600, ploidy=8, n_pos=16, depth=100, temps=(0.01, 0.1, 0.5, 1.0), steps=300),
+    "cfg3d": dict(n_items=592, ploidy=8, n_pos=16, depth=133, temps=(0.01, 0.1, 0.5, 1.0), steps=300),   # depth 100 at every SNV
+    "cfg1d": dict(n_items=20000, ploidy=4, n_pos=8, depth=53, temps=(1.0,), steps=1500),                 # depth 40 at every SNV
     "cfg1": dict(n_items=20000, ploidy=4, n_pos=8, depth=40, temps=(1.0,), steps=1500),
     "hex2": dict(n_items=4000, ploidy=6, n_pos=8, depth=40, temps=(0.2, 1.0), steps=1500),
 }
