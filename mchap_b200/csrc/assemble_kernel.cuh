@@ -99,7 +99,14 @@ struct AsmArgs {
     // halves their shared memory per warp and lets twice as many warps share an SM.
     double *rt_backing;          // [grid warps][rt_stride], only if CH >= 2
     int64_t rt_stride;
+    double *q_backing;           // [grid warps][q_stride] = [tmax][pmax][UPAD] rows + 2 spare rows, only if CH >= 3
+    int64_t q_stride;
 };
+
+// Kernels of three and more read chunks also keep the double-precision product rows q[slot][h][r]
+// in global memory, every state slot in its own place (the resident-slot swap then moves only the
+// float32 shadows, keys and memo tables): configs[3] goes from 40 to 30 KB of shared memory per warp.
+#define MCHB_ASM_Q_GLOBAL(CH) ((CH) >= 3)
 
 template <int CH>
 __device__ __forceinline__ double *asm_rt(const AsmArgs &a, unsigned char *sm) {
@@ -371,7 +378,7 @@ __device__ __noinline__ void slot_copy(const AsmArgs &a, unsigned char *sm, int 
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char *back = a.slot_backing + ((size_t)warp_global * a.tmax + slot) * a.slot_bytes;
     const int32_t offs[7] = {a.o_q, a.o_mcache, a.o_key, a.o_scache, a.o_q32, a.o_rpc, a.o_epoch};
-    const int32_t lens[7] = {a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, MCHB_SCACHE_N(CH) * (int)sizeof(ScEntry),
+    const int32_t lens[7] = {MCHB_ASM_Q_GLOBAL(CH) ? 0 : a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, MCHB_SCACHE_N(CH) * (int)sizeof(ScEntry),
                              a.pmax * UPAD * 4, UPAD * 4, 8};
     __syncwarp();
     size_t boff = 0;
@@ -408,12 +415,22 @@ struct AsmCtx {
     long long evals;
     int prof_t = 0;  // index of the temperature being stepped
     int n_acc;       // proposals accepted by the mutation compound step under way
+    int qslot = 0;   // state slot behind the resident position 0 (resident-slot swap with q in global memory)
 
     __device__ __forceinline__ AsmCtx(const AsmArgs &args, unsigned char *s, int l) : a(args), sm(s), lane(l) {}
 
     __device__ __forceinline__ double *Rt() const { return asm_rt<CH>(a, sm); }
     __device__ __forceinline__ double *cnt() const { return reinterpret_cast<double *>(sm + a.o_cnt); }
-    __device__ __forceinline__ double *q() const { return reinterpret_cast<double *>(sm + a.o_q); }
+    // product rows of the resident state slot(s): shared memory, or (three and more chunks) this
+    // warp's region of q_backing, where qslot is the slot the resident position 0 stands for
+    __device__ __forceinline__ double *qwarp() const {
+        const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        return a.q_backing + (size_t)warp_global * a.q_stride;
+    }
+    __device__ __forceinline__ double *q() const {
+        if (!MCHB_ASM_Q_GLOBAL(CH)) return reinterpret_cast<double *>(sm + a.o_q);
+        return qwarp() + (size_t)qslot * a.pmax * UPAD;
+    }
     __device__ __forceinline__ double *dist() const { return reinterpret_cast<double *>(sm + a.o_dist); }
     __device__ __forceinline__ double *oll() const { return reinterpret_cast<double *>(sm + a.o_oll); }
     __device__ __forceinline__ double *opr() const { return reinterpret_cast<double *>(sm + a.o_opr); }
@@ -439,7 +456,7 @@ struct AsmCtx {
     __device__ __forceinline__ const uint64_t *slot_keys(int s) const {
         if (CH < 2 || a.tres >= a.tmax) return keys(s);  // (the CH = 1 kernels never swap: see launch_assemble)
         const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const size_t key_off = (size_t)a.pmax * UPAD * 8 + (size_t)2 * a.pmax * a.nmax * 8;  // after q and mcache
+        const size_t key_off = (MCHB_ASM_Q_GLOBAL(CH) ? 0 : (size_t)a.pmax * UPAD * 8) + (size_t)2 * a.pmax * a.nmax * 8;  // after q and mcache
         return reinterpret_cast<const uint64_t *>(a.slot_backing + ((size_t)warp_global * a.tmax + s) * a.slot_bytes + key_off);
     }
 
@@ -469,7 +486,10 @@ struct AsmCtx {
     }
     __device__ __forceinline__ double *qrow_lane(int s, int h) const { return q() + (size_t)(s * P + h) * UPAD + lane; }
     // spare rows (two per warp) that hold the old rows of a proposal while it is installed
-    __device__ __forceinline__ double *spare_lane(int k) const { return q() + (size_t)(a.tres * a.pmax + k) * UPAD + lane; }
+    __device__ __forceinline__ double *spare_lane(int k) const {
+        if (MCHB_ASM_Q_GLOBAL(CH)) return qwarp() + (size_t)(a.tmax * a.pmax + k) * UPAD + lane;
+        return q() + (size_t)(a.tres * a.pmax + k) * UPAD + lane;
+    }
 
     __device__ __forceinline__ float *q32() const { return reinterpret_cast<float *>(sm + a.o_q32); }
     __device__ __forceinline__ float *rat() const { return reinterpret_cast<float *>(sm + a.o_rat); }
@@ -1691,6 +1711,7 @@ __global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH))
                 // one resident slot, the others in the backing store (never in the CH = 1 kernels,
                 // whose hot loop stays free of the swap code)
                 const bool swap = CH >= 2 && a.tres < a.tmax && T > 1;
+                c.qslot = 0;
                 if (swap) {
                     uint64_t *kk = reinterpret_cast<uint64_t *>(c.oll());  // the initial keys survive the slot loads
                     for (int h = lane; h < P; h += 32) kk[h] = k0[h];
@@ -1698,6 +1719,7 @@ __global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH))
 #pragma unroll 1
                     for (int t = 0; t < T; t++) {
                         slot_copy<CH>(a, c.sm, lane, t, false);
+                        c.qslot = t;
 #pragma unroll 1
                         for (int h = 0; h < P; h++) c.commit(0, h, kk[h]);
                         slot_copy<CH>(a, c.sm, lane, t, true);
@@ -1737,6 +1759,7 @@ __global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH))
                         const long long pc0 = MCHB_PROF_CLOCK();
                         if (swap) {
                             slot_copy<CH>(a, c.sm, lane, s, false);
+                            c.qslot = s;
                             s = 0;
                         }
                         const long long pc1 = MCHB_PROF_CLOCK();

@@ -60,6 +60,7 @@ enum Slot {
     S_EITEMS, S_ECALLS, S_EPROBS, S_ENALL, S_EREADS, S_ECOUNTS, S_ERESULTS,
     S_BACKING0, S_BACKING1, S_BACKING2, S_BACKING3, S_BACKING4, S_BACKING5, S_BACKING6, S_BACKING7, S_BACKING8, S_BACKING9, S_BACKING10, S_BACKING11, S_BACKING12, S_BACKING13,
     S_RTBACK0, S_RTBACK1, S_RTBACK2, S_RTBACK3, S_RTBACK4, S_RTBACK5, S_RTBACK6, S_RTBACK7, S_RTBACK8, S_RTBACK9, S_RTBACK10, S_RTBACK11, S_RTBACK12, S_RTBACK13,
+    S_QBACK0, S_QBACK1, S_QBACK2, S_QBACK3, S_QBACK4, S_QBACK5, S_QBACK6, S_QBACK7, S_QBACK8, S_QBACK9, S_QBACK10, S_QBACK11, S_QBACK12, S_QBACK13,
     S_NSLOTS
 };
 
@@ -412,7 +413,7 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     // Rt at 0 in the one-chunk kernels; the kernels of larger items keep it in global memory (L2)
     take(ch >= 2 ? 0 : (size_t)g.nmax * g.amax * upad * 8, 16);
     args.o_cnt = take(upad * 8, 8);
-    args.o_q = take(((size_t)tres * g.pmax + 2) * upad * 8, 8);  // + 2 spare rows
+    args.o_q = take(MCHB_ASM_Q_GLOBAL(ch) ? 0 : ((size_t)tres * g.pmax + 2) * upad * 8, 8);  // + 2 spare rows
     args.o_dist = take((size_t)g.nmax * g.amax * 8, 8);
     args.o_oll = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_opr = take((size_t)(g.maxopt + 1) * 8, 8);
@@ -453,9 +454,17 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
     // then one resident slot, the others swapped through a backing store in global memory
     int tres = g.tmax;
     size_t per_warp = asm_layout(g, CH, tres, args);
-    if (CH >= 2 && g.tmax > 1 && per_warp * 4 > (size_t)h->smem_optin) {
-        tres = 1;
-        per_warp = asm_layout(g, CH, tres, args);
+    if (CH >= 2 && g.tmax > 1) {
+        // one resident slot when all of them do not fit four warps, or (three and more chunks: a
+        // handful of warps per SM at best) when swapping lets an SM hold 1.5 times as many warps
+        AsmArgs tmp = args;
+        const size_t per_warp_swap = asm_layout(g, CH, 1, tmp);
+        const size_t room = (size_t)h->smem_optin;
+        const size_t w_full = std::min<size_t>(16, room / per_warp), w_swap = std::min<size_t>(16, room / per_warp_swap);
+        if (per_warp * 4 > room || (CH >= 3 && 2 * w_swap >= 3 * w_full)) {
+            tres = 1;
+            per_warp = asm_layout(g, CH, tres, args);
+        }
     }
     // warps per CTA: the value that keeps most warps resident per SM (shared memory and registers
     // both count: the occupancy query knows the kernel's register allocation); ties go to 4, then
@@ -495,7 +504,7 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
     if (tres < g.tmax) {
         const size_t upad = (size_t)CH * 32;
         auto r8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
-        const size_t slot_bytes = (r8(g.pmax * upad * 8) + r8((size_t)2 * g.pmax * g.nmax * 8) + r8((size_t)g.pmax * 8) +
+        const size_t slot_bytes = (r8(MCHB_ASM_Q_GLOBAL(CH) ? 0 : g.pmax * upad * 8) + r8((size_t)2 * g.pmax * g.nmax * 8) + r8((size_t)g.pmax * 8) +
                                    r8(MCHB_SCACHE_N(CH) * sizeof(ScEntry)) + r8(g.pmax * upad * 4) + r8(upad * 4) + r8(8) + 15) &
                                   ~(size_t)15;
         void *back;
@@ -513,6 +522,16 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
         if (rc) return rc;
         args.rt_backing = (double *)back;
         args.rt_stride = (int64_t)rt_elems;
+    }
+    args.q_backing = nullptr;
+    args.q_stride = 0;
+    if (MCHB_ASM_Q_GLOBAL(CH)) {
+        const size_t q_elems = ((size_t)g.tmax * g.pmax + 2) * CH * 32;
+        void *back;
+        int rc = ensure(h, backing_slot - S_BACKING0 + S_QBACK0, q_elems * 8 * (size_t)grid * warps_per_cta, &back);
+        if (rc) return rc;
+        args.q_backing = (double *)back;
+        args.q_stride = (int64_t)q_elems;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
