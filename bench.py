@@ -50,8 +50,9 @@ WORKLOAD = ("synthetic tetraploid assemble: 10k loci x 8 SNVs x 100 samples, dep
             "2 chains x 1500 steps")
 
 # DRAM bytes per (locus, sample) item of assemble_kernel<1,false>, from the committed ncu capture
-# (profiles/README.md): dram__bytes_read.sum + dram__bytes_write.sum of a 7104-item launch
-NCU_DRAM_BYTES_PER_ITEM = 118465.0
+# (profiles/r02_c1_ncu_raw.csv): dram__bytes_read.sum + dram__bytes_write.sum = 817.2 MB for the 6801 items
+# of that launch (the items with <= 32 distinct reads of a 14208-item batch at depth 40)
+NCU_DRAM_BYTES_PER_ITEM = 120164.0
 
 
 def parse_args():
@@ -419,8 +420,18 @@ def config_octoploid(R, dev, args, peak_tf, cpu):
     P, N, depth, temps, steps, chains = 8, 16, 100, (0.01, 0.1, 0.5, 1.0), 1500, 2
     if args.octoploid_steps:
         steps = args.octoploid_steps
-    n = 21 * dev.sm_count           # three waves of the kernel (7 warps per SM at this shape)
     frag = fragments(depth, N)
+    # three full waves of the kernel: a probe call tells how many items (warps) the GPU holds at once at
+    # this shape (the real workload, loci sharded over the GPUs, runs hundreds of waves)
+    pb = synth_items(64, ploidy=P, n_pos=N, depth=frag, seed=7)
+    ptable, plens = break_table(N)
+    pparams, pkeep = make_assemble_params(2, 1, 0.999, 0.5, 0.5, 1.0, ptable, plens, list(temps))
+    pitems = uniform_assemble_items(pb.offsets, N, pb.max_allele, P, 1, 2, n_temps=len(temps), seed=SEED)
+    dev.assemble_call(pitems, pparams, pb.reads.reshape(-1), pb.counts, np.ascontiguousarray(pb.n_alleles.reshape(-1)), None,
+                      np.empty(64 * 2 * P * N, dtype=np.int8), np.empty(64 * 2),
+                      (pb.reads.size, pb.counts.size, pb.n_alleles.size, 0, 64 * 2 * P * N, 64 * 2), mem=L.MEM_HOST)
+    resident = max(dev.last_resident_warps, dev.sm_count)
+    n = 3 * resident
     b = synth_items(n, ploidy=P, n_pos=N, depth=frag, seed=31337 + R.rank)
     items = uniform_assemble_items(b.offsets, N, b.max_allele, P, chains, steps, n_temps=len(temps), seed=SEED)
     table, lens = break_table(N)
@@ -461,7 +472,7 @@ def config_octoploid(R, dev, args, peak_tf, cpu):
         "e2e": {"value": R.world * n_steps * reps / dt_max, "unit": UNIT,
                 "h2d_bytes_per_step": int(reads.nbytes + cnts.nbytes + nall.nbytes + items.nbytes),
                 "d2h_bytes_per_step": int(g_len + 8 * l_len + 24 * n), "ms_per_step": 1e3 * dt_max / reps},
-        "gpu_launches": launches, "mean_unique_reads": float(b.n_reads().mean()),
+        "gpu_launches": launches, "mean_unique_reads": float(b.n_reads().mean()), "resident_items_per_gpu": resident,
         "llk_evals_per_mcmc_step": float(res0["llk_evals"].sum()) / n_steps,
         "roofline": fp64_roofline(flops, kms * 1e-3, peak_tf, "assemble_kernel<CH = ceil(U / 32)>"),
     }
@@ -708,8 +719,8 @@ def run_b200(args, rank, world):
         pass
     roofline = fp64_roofline(flops, dev_time, peak_tf, "assemble_kernel<1> + assemble_kernel<2> (items with <= 32 / 33-64 distinct reads)", {
         "traffic": NCU_DRAM_BYTES_PER_ITEM * items_per_step, "traffic_per_item": NCU_DRAM_BYTES_PER_ITEM,
-        "traffic_source": "profiles/r02_cfg1_full_ncu_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) of one "
-                          "`ncu --set full` launch of assemble_kernel<1,false> / its 7104 items, scaled to the %d items "
+        "traffic_source": "profiles/r02_c1_ncu_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) of one "
+                          "`ncu --set full` launch of assemble_kernel<1,false> / its 6801 items, scaled to the %d items "
                           "of one bench step; algorithmic bytes per item = %.0f" % (
                               items_per_step, (in_bytes + out_bytes) / items_per_step),
         "llk_evals_per_mcmc_step": evals / (K * items_per_step * CHAINS * MCMC_STEPS),

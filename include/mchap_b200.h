@@ -80,6 +80,9 @@ int32_t mchb_last_host_chunks(const mchb_handle *h);
 /* the cudaStream_t the handle launches on (for external event timing) */
 void *mchb_stream(const mchb_handle *h);
 int mchb_sm_count(const mchb_handle *h);
+/* warps the GPU held at once in the most populated assemble launch of the last call (one warp = one item):
+ * callers that size batches in whole waves avoid the tail of a partially filled last wave */
+int32_t mchb_last_resident_warps(const mchb_handle *h);
 
 /* Page-locked host memory for the bulk arrays of MCHB_MEM_HOST calls (no reference counterpart: the
  * reference never leaves the host).  Copies from / to such buffers run at the full PCIe rate and

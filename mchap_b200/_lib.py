@@ -196,7 +196,7 @@ SYMBOLS = [
     "mchb_genotype_likelihoods_batch", "mchb_genotype_posteriors_batch", "mchb_call_mcmc_batch",
     "mchb_trace_tally_batch", "mchb_assemble_tally_batch", "mchb_call_trace_tally_batch",
     "mchb_call_mcmc_tally_batch", "mchb_encode_reads_batch", "mchb_encode_assemble_tally_batch",
-    "mchb_mec_batch", "mchb_host_alloc", "mchb_host_free", "mchb_debug_counters",
+    "mchb_mec_batch", "mchb_host_alloc", "mchb_host_free", "mchb_debug_counters", "mchb_last_resident_warps",
 ]
 
 
@@ -235,6 +235,8 @@ def load():
         L.mchb_stream.argtypes = [vp]
         L.mchb_sm_count.restype = C.c_int
         L.mchb_sm_count.argtypes = [vp]
+        L.mchb_last_resident_warps.restype = C.c_int32
+        L.mchb_last_resident_warps.argtypes = [vp]
         L.mchb_measure_fp64_peak.restype = C.c_int
         L.mchb_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.mchb_mt19937_words.restype = C.c_int

@@ -106,6 +106,11 @@ class Device:
         return int(self._lib.mchb_last_host_chunks(self._h))
 
     @property
+    def last_resident_warps(self):
+        """Items (warps) the GPU held at once in the largest assemble launch of the last call."""
+        return int(self._lib.mchb_last_resident_warps(self._h))
+
+    @property
     def sm_count(self):
         return int(self._lib.mchb_sm_count(self._h))
 

@@ -30,10 +30,11 @@
 #define MCHB_ASM_MINBLOCKS 4
 #endif
 // Launch bounds per read-chunk count.  One and two chunks: 4 CTAs of 4 warps, 128 registers (16 warps
-// per SM; shared memory allows as many at the headline shape).  Three and four chunks: shared memory
-// leaves at most 8 warps per SM, 255 registers.  Eight chunks: one or two warps per SM.
-#define MCHB_ASM_MAXTHREADS(CH) 128
-#define MCHB_ASM_MINCTAS(CH) ((CH) <= 2 ? MCHB_ASM_MINBLOCKS : ((CH) <= 4 ? 2 : 1))
+// per SM; shared memory allows as many at the headline shape).  Three and four chunks: CTAs of one or
+// two warps, 204 registers, so that the 10 warps per SM that shared memory allows at configs[3] fit
+// the register file.  Eight and more chunks: one or two warps per SM, no register cap.
+#define MCHB_ASM_MAXTHREADS(CH) (((CH) == 3 || (CH) == 4) ? 64 : 128)
+#define MCHB_ASM_MINCTAS(CH) ((CH) <= 2 ? MCHB_ASM_MINBLOCKS : ((CH) <= 4 ? 5 : 1))
 
 namespace mchb {
 
@@ -107,6 +108,11 @@ struct AsmArgs {
 // in global memory, every state slot in its own place (the resident-slot swap then moves only the
 // float32 shadows, keys and memo tables): configs[3] goes from 40 to 30 KB of shared memory per warp.
 #define MCHB_ASM_Q_GLOBAL(CH) ((CH) >= 3)
+// ... and hold one direction of the float32 allele-ratio table, rat[j][r] = fl(R[j][1] / R[j][0]); the
+// other direction is its correctly rounded reciprocal, taken on the fly (one rounding more per factor,
+// accounted for in the error bounds of assemble_item_setup).  Ratios below the float32 normal range are
+// stored as 0 so that no denormal is ever inverted.
+#define MCHB_ASM_RAT_HALF(CH) ((CH) >= 3)
 
 template <int CH>
 __device__ __forceinline__ double *asm_rt(const AsmArgs &a, unsigned char *sm) {
@@ -860,12 +866,14 @@ struct AsmCtx {
                     // make the sub-step needy; above that the relative error stays below 1e-3.
                     const float *qh = q32() + (size_t)(s * P + h) * UPAD;
                     const float *rc = reinterpret_cast<const float *>(sm + a.o_rpc) + (size_t)s * UPAD;
-                    const float *rt = rat() + (size_t)(j * 2 + (cur & 1)) * UPAD;
+                    const float *rt = rat() + (size_t)(MCHB_ASM_RAT_HALF(CH) ? j : j * 2 + (cur & 1)) * UPAD;
                     const float *cw = c32();
 #pragma unroll 2
                     for (int r = 0; r < U; r++) {
                         const float rc_r = rc[r];
-                        const float rp = fmaf(qh[r], rt[r] - 1.0f, rc_r);
+                        float rt_r = rt[r];
+                        if (MCHB_ASM_RAT_HALF(CH) && (cur & 1)) rt_r = __frcp_rn(rt_r);
+                        const float rp = fmaf(qh[r], rt_r - 1.0f, rc_r);
                         sane = sane && (rp > MCHB_SCREEN_MIN_RATIO * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
                         a32f = fmaf(__logf(rp), cw[r], a32f);
                     }
@@ -1109,8 +1117,14 @@ struct AsmCtx {
                         const int c0 = (int)((k0 >> jp) & 1ull);
 #pragma unroll
                         for (int ch = 0; ch < CH; ch++) {
-                            ra[ch] *= rt[(jp * 2 + c0) * UPAD + ch * 32];        // h0 takes h1's allele
-                            rb[ch] *= rt[(jp * 2 + (c0 ^ 1)) * UPAD + ch * 32];  // h1 takes h0's allele
+                            if (MCHB_ASM_RAT_HALF(CH)) {
+                                const float v01 = rt[jp * UPAD + ch * 32], v10 = __frcp_rn(v01);
+                                ra[ch] *= c0 ? v10 : v01;  // h0 takes h1's allele
+                                rb[ch] *= c0 ? v01 : v10;  // h1 takes h0's allele
+                            } else {
+                                ra[ch] *= rt[(jp * 2 + c0) * UPAD + ch * 32];        // h0 takes h1's allele
+                                rb[ch] *= rt[(jp * 2 + (c0 ^ 1)) * UPAD + ch * 32];  // h1 takes h0's allele
+                            }
                         }
                     }
                     float acc = 0.f;
@@ -1522,8 +1536,14 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
             const int k = i / UPAD, r = i - k * UPAD;
             const double r0 = Rt[(k * A + 0) * UPAD + r];
             const double r1 = A > 1 ? Rt[(k * A + 1) * UPAD + r] : r0;
-            rat[(k * 2 + 0) * UPAD + r] = (float)(r1 / r0);  // current allele 0 -> 1
-            rat[(k * 2 + 1) * UPAD + r] = (float)(r0 / r1);  // current allele 1 -> 0
+            if (MCHB_ASM_RAT_HALF(CH)) {
+                float f01 = (float)(r1 / r0);
+                if (fabsf(f01) < 1.17549435e-38f) f01 = 0.f;  // (NaN stays NaN: the comparison is false)
+                rat[k * UPAD + r] = f01;
+            } else {
+                rat[(k * 2 + 0) * UPAD + r] = (float)(r1 / r0);  // current allele 0 -> 1
+                rat[(k * 2 + 1) * UPAD + r] = (float)(r0 / r1);  // current allele 1 -> 0
+            }
         }
         double csum = 0.0;
         for (int r = lane; r < UPAD; r += 32) {
@@ -1534,16 +1554,17 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
         if (lane == 0) {
             // Bounds of |screened - exact| log-likelihood, u = 2^-24:
             //  mutation: a read's screened probability fma(q32[h], rat - 1, rpc) has relative error
-            //    <= 1.001 u ((P + 2) rpc / rp + 4) with rpc / rp <= 1.5 / MCHB_SCREEN_MIN_RATIO under the
+            //    <= 1.001 u ((P + 2) rpc / rp + 5) with rpc / rp <= 1.5 / MCHB_SCREEN_MIN_RATIO under the
             //    `sane` test, i.e. <= 9.0e-4 (P + 2); log(1 + e) <= 1.02 e; __logf errs by <= 3.2e-5 on
             //    (1e-30, 1e30); the float32 fma accumulation over U reads by <= 4.3e-6 U per unit count;
             //  structural: products and sums of positive float32 values, relative error
-            //    <= 1.001 u (2 N + P + 1); accumulation over CH chunks per lane.
+            //    <= 1.001 u (3 N + P + 1) (a factor: u for the stored ratio, u for its reciprocal where
+            //    only one direction is stored, u for the product); accumulation over CH chunks per lane.
             const double umax_reads = (double)U;
             //  both: float32 underflow of a term (<= 2^-126 against rp > 1e-30): 1.2e-8 per operation.
             const double under = 1.2e-8 * (double)(N + P + 2);
             scv[SC_ERR_MUT] = csum * (1.02 * ((double)(P + 2) * 9.0e-4) + 3.2e-5 + 4.3e-6 * umax_reads + under);
-            scv[SC_ERR_STR] = csum * (1.02 * 6.0e-8 * (double)(2 * N + P + 1) + 3.2e-5 + 4.3e-6 * (double)(CH + 1) + under);
+            scv[SC_ERR_STR] = csum * (1.02 * 6.0e-8 * (double)(3 * N + P + 1) + 3.2e-5 + 4.3e-6 * (double)(CH + 1) + under);
         }
         __syncwarp();
     }

@@ -44,6 +44,8 @@ struct mchb_handle {
     float kernel_ms = 0.f;
     int32_t launches = 0;
     int32_t host_chunks = 1;
+    int32_t resident_warps = 0;   // warps the GPU holds at once in the most populated assemble launch of the last call
+    int32_t resident_class_items = 0;
     int64_t last_trace_len = 0;  // int8 elements of the trace left in scratch by mchb_assemble_tally_batch
     int64_t last_call_trace_len = 0;  // int32 elements left by mchb_call_mcmc_tally_batch
     std::vector<DevBuf> bufs;  // scratch slots, grown on demand
@@ -148,6 +150,8 @@ void begin_call(mchb_handle *h) {
     h->kernel_ms = 0.f;
     h->launches = 0;
     h->host_chunks = 1;
+    h->resident_warps = 0;
+    h->resident_class_items = 0;
 }
 
 }  // namespace
@@ -212,6 +216,7 @@ int32_t mchb_last_kernel_launches(const mchb_handle *h) { return h ? h->launches
 int32_t mchb_last_host_chunks(const mchb_handle *h) { return h ? h->host_chunks : 0; }
 void *mchb_stream(const mchb_handle *h) { return h ? (void *)h->stream : nullptr; }
 int mchb_sm_count(const mchb_handle *h) { return h ? h->sm_count : 0; }
+int32_t mchb_last_resident_warps(const mchb_handle *h) { return h ? h->resident_warps : 0; }
 
 int mchb_host_alloc(mchb_handle *h, int64_t bytes, void **out) {
     if (!h || !out || bytes < 0) return MCHB_ERR_ARGUMENT;
@@ -432,7 +437,7 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     args.o_ivp = take((size_t)g.nmax + 2, 1);
     args.o_ring = take(128 * 4, 4);
     args.o_q32 = take(((size_t)tres * g.pmax + 2) * upad * 4, 4);
-    args.o_rat = take((size_t)g.nmax * 2 * upad * 4, 4);
+    args.o_rat = take((size_t)g.nmax * (MCHB_ASM_RAT_HALF(ch) ? 1 : 2) * upad * 4, 4);
     args.o_c32 = take(upad * 4, 4);
     args.o_rpc = take((size_t)tres * upad * 4, 4);
     args.o_bcs = take((size_t)(g.maxopt + 1) * 8, 8);
@@ -489,6 +494,10 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
     }
     const size_t smem = per_warp * warps_per_cta;
     CK(cudaFuncSetAttribute(assemble_kernel<CH, PRIOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_items_class > h->resident_class_items) {
+        h->resident_class_items = n_items_class;
+        h->resident_warps = (int32_t)(h->sm_count * ctas_per_sm * warps_per_cta);
+    }
     long long want = ((long long)n_items_class + warps_per_cta - 1) / warps_per_cta;
     long long grid = std::min<long long>(want, (long long)h->sm_count * ctas_per_sm);
     if (grid < 1) grid = 1;

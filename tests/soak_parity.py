@@ -86,3 +86,10 @@ if __name__ == "__main__":
     run_shape("tetraploid 12 SNV depth 150 (64+ unique reads)", n // 3, s // 2, 4, 12, 150, seed=106)
     run_shape("octoploid 16 SNV depth 100, 4 temperatures (configs[3])", max(n // 30, 8), max(s // 8, 20), 8, 16, 100,
               temps=(0.01, 0.1, 0.5, 1.0), seed=107)
+    # round 2: depth 40 / 100 at every SNV (bench.py's workloads), hot mode over many steps, Rt and the
+    # product rows in global memory, a heated replica with the Dirichlet-multinomial prior
+    run_shape("tetraploid 8 SNV, 53 fragments (bench headline)", n, s, 4, 8, 53, seed=108)
+    run_shape("octoploid 16 SNV, 133 fragments, 4 temperatures (bench configs[3])", max(n // 30, 8), max(s // 4, 20), 8, 16,
+              133, temps=(0.01, 0.1, 0.5, 1.0), seed=109)
+    run_shape("hexaploid 8 SNV, 80 fragments, temperatures 0.05/0.3/1, inbreeding 0.1", n // 6, s // 2, 6, 8, 80,
+              temps=(0.05, 0.3, 1.0), inbreeding=0.1, seed=110)

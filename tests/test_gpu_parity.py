@@ -631,6 +631,13 @@ def _adversarial_reads(kind, rng, n_items, ploidy, n_pos, depth):
     ("counts", 4, 8, 30, (1.0,), None),
     ("counts", 6, 6, 30, (0.01, 0.1, 0.5, 1.0), None),
     ("plain", 8, 4, 30, (0.01, 1.0), None),       # coldest temperature allowed by the CLIs' docs
+    # three and four read chunks: Rt and the product rows in global memory, one direction of the ratio
+    # table (the other is its reciprocal), the serial exact tier only
+    ("phred", 4, 8, 90, (1.0,), None),
+    ("phred", 6, 10, 120, (0.1, 1.0), 0.1),
+    ("wide", 4, 8, 100, (0.2, 1.0), None),
+    ("zeros", 4, 6, 110, (0.05, 1.0), None),
+    ("ratio_one", 8, 6, 70, (1.0,), None),
 ])
 def test_assemble_screening_adversarial_vs_oracle(dev, oracle, kind, ploidy, n_pos, depth, temps, inbreeding):
     """the float32 screening (bi-allelic fast path) must never change a decision on
