@@ -1094,11 +1094,14 @@ struct AsmCtx {
             const bool try_screen = nf < 16 || (nf & 15) == 0;
             __syncwarp();
             if (lane == 0) *fails = nf + 1;
+            double my_d32 = 0.0;   // lane i: screened (llk_i - llk) + prior ratio of option i; NaN: not usable
+            bool screened = false;
             if (B == 1 && n_options <= 32 && try_screen) {
                 const float *qs = q32() + (size_t)(s * P) * UPAD + lane;
                 const float *rt = rat() + lane;
                 const float *cw = c32() + lane;
                 smax = -INFINITY;
+                screened = true;
 #pragma unroll 1
                 for (int k = 0; k < n_options; k++) {
                     const int h0 = o0[k], h1 = o1[k];
@@ -1149,9 +1152,11 @@ struct AsmCtx {
                     // the proposal ratio is log(1 / n_reverse) - log(1 / n_options) <= log(n_options): the
                     // bound spares the screening pass the reverse-move count of every option
                     const double lprop = -log_proposal;
-                    const double mh32 = ((a32 - llk) + lprior_ratio) * temp + lprop;
+                    const double d32 = (a32 - llk) + lprior_ratio;
+                    const double mh32 = d32 * temp + lprop;
                     smax = sane ? fmax(smax, mh32) : INFINITY;  // fmax ignores NaN: treat NaN as inconclusive
                     if (isnan(mh32)) smax = INFINITY;
+                    if (lane == k) my_d32 = sane ? d32 : NAN;
                 }
             }
             __syncwarp();
@@ -1170,6 +1175,61 @@ struct AsmCtx {
                 if (lane == 0) *fails = 0;
                 __syncwarp();
                 return;
+            }
+            // ---- the categorical draw by interval arithmetic.  The step picks the first k whose
+            // cumulative sum c_k = sum_{i<=k} exp(min(0, mh_i)) / n exceeds u ("stay" has the rest of
+            // the mass).  Every mh_i is known to within d = temp * SC_ERR_STR + slack of its screened
+            // value (here with the option's true proposal ratio), so c_k lies between the cumulative
+            // sums of exp(min(0, mh32_i -+ d)) / n: when the upper sum up to k - 1 is below u and the
+            // lower sum up to k is above u the choice is k whatever the exact values are — only the
+            // chosen option's log-likelihood (the new state's) is then evaluated exactly; when the
+            // upper sum of all options is below u the step stays.  Anything else is decided by the
+            // exact path below.  (Heated replicas: almost every structural step ends here.)
+            if (screened && u > 0.0 && u < 0.99999999999999911182) {
+                const int n_ret = structural_options(my_lin, lout, P, step_type, nullptr, nullptr);
+                const bool mine = lane < n_options;
+                const double dlt = temp * sc()[SC_ERR_STR] + MCHB_SCREEN_SLACK;
+                const double mh32 = my_d32 * temp + (LOG_INV_INT[mine ? n_ret : 1] - log_proposal);
+                const bool usable = mine && !isnan(mh32);
+                const double ln_opts = LOG_INT[n_options];
+                double lo = 0.0, hi = 0.0;
+                if (mine) {
+                    hi = dexp(-ln_opts);  // unusable option: anything up to 1 / n
+                    if (usable) {
+                        lo = dexp(fmin(0.0, mh32 - dlt) - ln_opts);
+                        hi = dexp(fmin(0.0, mh32 + dlt) - ln_opts);
+                    }
+                }
+                double slo = lo, shi = hi;  // inclusive prefix sums over the options
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double a_ = __shfl_up_sync(MCHB_FULL, slo, o), b_ = __shfl_up_sync(MCHB_FULL, shi, o);
+                    if (lane >= o) {
+                        slo += a_;
+                        shi += b_;
+                    }
+                }
+                const double eps = 1e-12;  // roundings of the reference's own cumulative sum
+                const bool is_k = mine && (shi - hi) + eps < u && slo - eps > u;
+                const unsigned pick = __ballot_sync(MCHB_FULL, is_k);
+                const double shi_all = __shfl_sync(MCHB_FULL, shi, n_options - 1);
+                if (pick != 0 || shi_all + eps < u) {
+                    evals += n_options;
+                    if (lane == 0) *fails = 0;
+                    __syncwarp();
+                    if (pick != 0) {
+                        const int choice = __ffs(pick) - 1;
+                        MCHB_PROF_ADD(prof_t, PK_STR_ACCEPT, 1);
+                        const int h0 = o0[choice], h1 = o1[choice];
+                        const uint64_t k0 = ks[h0], k1 = ks[h1];
+                        if (step_type == 0) commit(s, h1, (k0 & mask_in) | (k1 & ~mask_in));
+                        commit(s, h0, (k1 & mask_in) | (k0 & ~mask_in));
+                        llk = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
+                    } else {
+                        MCHB_PROF_ADD(prof_t, PK_STR_SCREEN_STAY, 1);
+                    }
+                    return;
+                }
             }
         }
         double my_la = -INFINITY;
