@@ -704,6 +704,128 @@ struct AsmCtx {
     // walks the reads in read order like likelihood.py:45-68); the first accepting lane commits
     // and the sub-steps behind it are re-evaluated from the new state.  A sub-step at a position
     // with more than two alleles is a barrier handled by the serial base_step.
+    // ------------------------------------------------------------------ hot mode of mutation.py:165-246
+    // The shuffled sub-steps of a replica that accepts most proposals, one after the other (lanes =
+    // reads).  Each bi-allelic sub-step is first screened in float32: the proposal's log-likelihood
+    // a32 = sum_r c_r logf(rpc_r + q32[h][r] (R_new / R_old - 1)) is within SC_ERR_MUT of the exact one.
+    // The exact step accepts iff exp(min(0, mh)) reaches t = u (current allele 1) or t = 1 - u
+    // (current allele 0); with d = temp * (error of a32 + error of the current state's value) + slack,
+    //   mh32 < log t - d  -> certainly rejected,   mh32 > log t + d  -> certainly accepted,
+    // anything else is decided exactly (install the row, eval_rows, the reference's arithmetic).
+    // After a certain acceptance the exact log-likelihood of the new state is not needed until a later
+    // decision is ambiguous or the compound step ends: until then the screened value a32 of the accepted
+    // proposal stands in for it (its error is the same SC_ERR_MUT, doubling d) and the exact value is
+    // evaluated from the rows when it is asked for — a deterministic function of the state, the
+    // value the reference carries.  Decisions, draws and evaluation counts are the reference's.
+    __device__ __forceinline__ void hot_compound_step(int s, int t, double temp, double &llk, int n) {
+        const uint16_t *pm = perm();
+        const uint8_t *na = nall();
+        uint64_t *ks = keys(s);
+        const double e_mut = sc()[SC_ERR_MUT];
+        bool known = true;   // llk is the exact log-likelihood of the current state
+        double l32 = 0.0;    // otherwise: the screened value of the proposal that was accepted last
+#pragma unroll 1
+        for (int i = 0; i < n && !err; i++) {
+            const int hj = pm[i];
+            const int h = hj >> 8, j = hj & 255;
+            const uint64_t kh = ks[h];
+            const int shift = B * j;
+            const int cur = (int)((uint32_t)(kh >> shift) & amask);
+            const double u = ws.next_double();
+            if (na[j] != 2 || cur >= 2) {
+                if (!known) {
+                    llk = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
+                    known = true;
+                }
+                base_step(s, h, j, na[j], temp, llk, u);
+                continue;
+            }
+            evals++;
+            const uint64_t kn = (kh & ~((uint64_t)amask << shift)) | ((uint64_t)(cur ^ 1) << shift);
+            // lanes 0..P-1 compare one haplotype each (jitutils.count_haplotype_copies 349-374)
+            const bool hl = lane < P;
+            const uint64_t myk = hl ? ks[lane] : 0ull;
+            const int copies_o = __popc(__ballot_sync(MCHB_FULL, hl && myk == kh));
+            const int copies_n = 1 + __popc(__ballot_sync(MCHB_FULL, hl && lane != h && myk == kn));
+            const double lprop = LOG_INT[copies_n] - LOG_INT[copies_o];
+            double lprior_ratio = 0.0;
+            if (PRIOR) lprior_ratio = prior_of_keys(ks, h, kn, -1, 0) - prior_of_keys(ks, -1, 0, -1, 0);
+            // ---- float32 screen of this proposal
+            float acc = 0.f;
+            bool ok = true;
+            {
+                const float *qh = q32() + (size_t)(s * P + h) * UPAD + lane;
+                const float *rc = reinterpret_cast<const float *>(sm + a.o_rpc) + (size_t)s * UPAD + lane;
+                const float *rt = rat() + (size_t)(MCHB_ASM_RAT_HALF(CH) ? j : j * 2 + (cur & 1)) * UPAD + lane;
+                const float *cw = c32() + lane;
+#pragma unroll
+                for (int ch = 0; ch < CH; ch++) {
+                    const float rc_r = rc[ch * 32];
+                    float rt_r = rt[ch * 32];
+                    if (MCHB_ASM_RAT_HALF(CH) && (cur & 1)) rt_r = __frcp_rn(rt_r);
+                    const float rp = fmaf(qh[ch * 32], rt_r - 1.0f, rc_r);
+                    ok = ok && (rp > MCHB_SCREEN_MIN_RATIO * rc_r) && (rp > 1e-30f) && (rp < 1e30f);
+                    acc = fmaf(__logf(rp), cw[ch * 32], acc);
+                }
+            }
+            const double a32 = warp_sum((double)acc);
+            const bool sane = __all_sync(MCHB_FULL, ok);
+            const double mh32 = ((a32 - (known ? llk : l32)) + lprior_ratio) * temp + lprop;
+            const double t_acc = (cur == 1) ? u : 1.0 - u;
+            const double thr = (double)__logf((float)t_acc);
+            const double dlt = temp * (known ? e_mut : 2.0 * e_mut) + MCHB_SCREEN_SLACK;
+            // (u away from 0 and 1: log t stays inside __logf's range and the cs1 <= u corner is excluded)
+            const bool decidable = sane && u > 8.8817841970012523e-16 && u < 0.99999999999999911182;
+            if (decidable && mh32 < thr - dlt) continue;  // certainly rejected
+            if (decidable && mh32 > thr + dlt) {          // certainly accepted
+                MCHB_PROF_ADD(prof_t, PK_MUT_ACCEPT, 1);
+                n_acc++;
+                commit(s, h, kn);
+                l32 = a32;
+                known = false;
+                continue;
+            }
+            // ---- decided exactly
+            if (!known) {
+                llk = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
+                known = true;
+            }
+            MCHB_PROF_ADD(prof_t, PK_T2A_EVALS, 1);
+            install_row(s, h, kn, 0);
+            const double llk_x = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
+            const double mh = ((llk_x - llk) + lprior_ratio) * temp + lprop;
+            const double la = np_minimum0(mh);
+            int choice;
+            if (la < -40.0 && u >= 1.1102230246251565e-16) {
+                choice = cur;
+            } else {
+                const double p_o = dexp(la - 0.0);
+                const double p_c = 1 - p_o;  // 1 - (0 + p_o)
+                const double cs0 = cur == 0 ? p_c : p_o;
+                const double cs1 = cs0 + (cur == 0 ? p_o : p_c);
+                choice = (cs1 <= u) ? 2 : ((cs0 <= u) ? 1 : 0);
+            }
+            if (choice == cur) {
+                restore_row(s, h, 0);
+            } else if (choice >= 2) {
+                restore_row(s, h, 0);
+                err = MCHB_ITEM_CHOICE_RANGE;
+            } else {
+                __syncwarp();
+                MCHB_PROF_ADD(prof_t, PK_MUT_ACCEPT, 1);
+                n_acc++;
+                ks[h] = kn;  // the row is already installed
+                llk = llk_x;
+                refresh_rpc(s);
+                bump_epoch(s);
+            }
+        }
+        if (!known && !err) llk = eval_rows<CH>(q() + (size_t)(s * P) * UPAD + lane, cnt() + lane, P);
+        __syncwarp();
+        if (lane == 0) hot()[4 * t] = n_acc;
+        __syncwarp();
+    }
+
     // Per-temperature history that steers the choice between equivalent code paths (never the
     // results): [4 t] accepted proposals of the previous mutation compound step at temperature t.
     __device__ __forceinline__ int32_t *hot() const { return reinterpret_cast<int32_t *>(sm + a.o_hot); }
@@ -798,6 +920,10 @@ struct AsmCtx {
         __syncwarp();
         const uint8_t *na = nall();
         uint64_t *ks = keys(s);
+        if (hot_mode) {
+            hot_compound_step(s, t, temp, llk, n);
+            return;
+        }
         const double *Rt0 = Rt();
         const double *q0 = q() + (size_t)(s * P) * UPAD;
         const double *cn = cnt();
@@ -807,7 +933,7 @@ struct AsmCtx {
         while (done < n && !err) {
             // screened quantities of this slot's sub-steps are still valid if the state is the
             // one they were computed for
-            const bool memo_ok = !hot_mode && epoch()[a.tres + s] == epoch()[s];
+            const bool memo_ok = epoch()[a.tres + s] == epoch()[s];
             const int i = done + lane;
             const bool active = i < n;
             const int hj = pm[active ? i : done];
@@ -858,8 +984,8 @@ struct AsmCtx {
                 // screened mh is below log(t) - (temp * SC_ERR_MUT + slack) is certainly rejected and needs no exact
                 // evaluation; everything else ("needy") is decided exactly below.
                 float a32f = 0.f;  // float32 accumulation: its rounding is part of SC_ERR_MUT
-                bool sane = !hot_mode;
-                if (!hot_mode) {
+                bool sane = true;
+                {
                     // rp_new = rp_cur + q[h] * (R_new / R_old - 1): one fused multiply-add per read.
                     // The subtraction hidden in it can lose relative accuracy when the proposal
                     // removes almost all of a read's probability, so reads with rp_new < 1e-4 rp_cur
@@ -880,7 +1006,7 @@ struct AsmCtx {
                 }
                 const double a32 = (double)a32f;
                 d32 = sane ? (a32 - llk) + lprior_ratio : INFINITY;  // +inf: never screened out
-                if (mine && !hot_mode) {
+                if (mine) {
                     mc[0] = d32;
                     mc[1] = lprop;
                 }
@@ -894,7 +1020,7 @@ struct AsmCtx {
                 lprior_ratio = prior_of_keys_lane(ks, h, kn) - prior_of_keys_lane(ks, -1, 0);
             // (the kernels of larger items always take the serial tier: their Rt lives in global memory
             // and the lane-per-sub-step loop of tier 2b would read it with 32 different rows per load)
-            if (CH >= 2 || hot_mode || __popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
+            if (CH >= 2 || __popc(needy) <= MCHB_EXACT_SERIAL_MAX) {
                 // ---- tier 2a: exact decisions for the needy sub-steps, in order (uniform code)
                 int completed = limit;
                 unsigned m = needy;
@@ -1018,7 +1144,7 @@ struct AsmCtx {
         // every bi-allelic sub-step was screened from one and the same state: keep the memo
         __syncwarp();
         if (lane == 0) {
-            if (!err && !hot_mode && epoch()[s] == epoch_at_start) epoch()[a.tres + s] = epoch_at_start;
+            if (!err && epoch()[s] == epoch_at_start) epoch()[a.tres + s] = epoch_at_start;
             hot()[4 * t] = n_acc;
         }
         __syncwarp();
