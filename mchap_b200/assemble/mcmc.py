@@ -98,6 +98,33 @@ def _sort_temperatures(temperatures):
     return temps
 
 
+# Every distinct seed of a call needs its own pre-generated MT19937 stream on the device (a few MB);
+# batches with more distinct per-item seeds than this run as consecutive sub-batches.
+MAX_DISTINCT_SEEDS = 1024
+
+
+def split_by_seeds(model, name, n, seeds, lists, kw):
+    """Run ``model.<name>`` over consecutive sub-batches of at most MAX_DISTINCT_SEEDS items when the
+    per-item ``seeds`` hold more distinct values than that; returns None when no split is needed.
+    Results are joined in order: a list, or (list, array, ...)."""
+    if seeds is None or n <= MAX_DISTINCT_SEEDS or len(np.unique(np.asarray(seeds))) <= MAX_DISTINCT_SEEDS:
+        return None
+    outs = []
+    for a in range(0, n, MAX_DISTINCT_SEEDS):
+        b = min(n, a + MAX_DISTINCT_SEEDS)
+        sub = {k: (None if v is None else v[a:b]) for k, v in lists.items()}
+        outs.append(getattr(model, name)(**sub, **kw))
+    if isinstance(outs[0], tuple):
+        joined = []
+        for o in outs:
+            joined.extend(o[0])
+        return (joined,) + tuple(np.concatenate([o[j] for o in outs]) for j in range(1, len(outs[0])))
+    joined = []
+    for o in outs:
+        joined.extend(o)
+    return joined
+
+
 def _settle(out, i, status, n, errors):
     """Handle the device status of item i: returns True when the item is fine; otherwise raises
     (errors='raise') or stores the exception in out[i] (errors='return')."""
@@ -259,6 +286,13 @@ class DenovoMCMC(object):
         assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(reads_list)
+        split = split_by_seeds(
+            self, "fit_batch", n, seeds,
+            dict(reads_list=reads_list, counts_list=counts_list, initial_list=initial_list, n_alleles_list=n_alleles_list,
+                 seeds=seeds, ploidy_list=ploidy_list, inbreeding_list=inbreeding_list, temperatures_list=temperatures_list),
+            dict(return_results=return_results, raw=raw, replay_words=replay_words, errors=errors))
+        if split is not None:
+            return split
         pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds, ploidy_list, inbreeding_list,
                         temperatures_list)
         items, go, lo = pk["items"], pk["genotypes_len"], pk["llks_len"]
@@ -359,6 +393,13 @@ class DenovoMCMC(object):
         dev = self.device or default_device()
         n = len(reads_list)
         burn = int(burn)
+        split = split_by_seeds(
+            self, "fit_posterior_batch", n, seeds,
+            dict(reads_list=reads_list, counts_list=counts_list, initial_list=initial_list, n_alleles_list=n_alleles_list,
+                 seeds=seeds, ploidy_list=ploidy_list, inbreeding_list=inbreeding_list, temperatures_list=temperatures_list),
+            dict(burn=burn, max_unique=max_unique, errors=errors))
+        if split is not None:
+            return split
         pk = self._pack(reads_list, counts_list, initial_list, n_alleles_list, seeds, ploidy_list, inbreeding_list,
                         temperatures_list)
         items = pk["items"]

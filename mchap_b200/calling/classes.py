@@ -249,6 +249,15 @@ class CallingMCMC(object):
         assert errors in ("raise", "return")
         dev = self.device or default_device()
         n = len(reads_list)
+        from ..assemble.mcmc import split_by_seeds
+
+        split = split_by_seeds(
+            self, "fit_batch", n, seeds,
+            dict(reads_list=reads_list, counts_list=counts_list, initial_list=initial_list,
+                 haplotypes_list=haplotypes_list, priors=priors, seeds=seeds, ploidy_list=ploidy_list),
+            dict(return_results=return_results, replay_words=replay_words, errors=errors))
+        if split is not None:
+            return split
         batch, haps, prs, ploidy, pmax, init = self._prepare(reads_list, counts_list, initial_list, haplotypes_list,
                                                              priors, seeds, ploidy_list)
         out = dev.call_mcmc(batch, self.steps, self.chains, self._step_type(), init, pmax, replay_words)

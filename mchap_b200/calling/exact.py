@@ -136,11 +136,14 @@ def posterior_allele_frequencies(posteriors, ploidy, n_alleles, device=None):
     Evaluated as posteriors of log(p) under no prior, which reproduces p up to normalisation."""
     dev = device or default_device()
     p = np.ascontiguousarray(posteriors, dtype=np.float64)
+    total = p.sum()
+    if not total > 0.0:   # all-zero posteriors: the reference's plain sums give zeros (exact.py:355-369)
+        z = np.zeros(int(n_alleles), dtype=np.float64)
+        return z, z.copy(), z.copy()
     items, _ = _posterior_items(len(p), ploidy, n_alleles, None)
     with np.errstate(divide="ignore"):
         lp = np.log(p)
     _, freqs, counts, occur = dev.genotype_posteriors(items, lp, None, len(p), int(n_alleles), with_frequencies=True)
-    total = p.sum()
     return freqs * total, counts * total, occur * total
 
 

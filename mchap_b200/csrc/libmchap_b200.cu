@@ -233,7 +233,23 @@ int mchb_host_free(mchb_handle *h, void *p) {
 }
 
 // ------------------------------------------------------------------------------------- RNG
+// One pre-generated stream per DISTINCT seed of the call (the CLIs seed every fit identically: one
+// stream of 1-3 MB serves the whole batch).  Per-item seeds multiply that: the total is bounded here,
+// loudly, instead of failing in cudaMalloc — callers with many distinct seeds split their batch
+// (the Python layer does: DenovoMCMC / CallingMCMC `seeds=`).
+#ifndef MCHB_STREAM_BUDGET
+#define MCHB_STREAM_BUDGET (16ull << 30)
+#endif
 static int fill_streams(mchb_handle *h, const std::vector<uint32_t> &seeds, int64_t len, uint32_t **words) {
+    if (len <= 0 || len > 0x7fffffffll) {
+        h->err = "MT19937 stream of " + std::to_string(len) + " words per seed is out of range";
+        return MCHB_ERR_ARGUMENT;
+    }
+    if ((unsigned long long)seeds.size() * (unsigned long long)len * 4ull > MCHB_STREAM_BUDGET) {
+        h->err = std::to_string(seeds.size()) + " distinct seeds x " + std::to_string(len) +
+                 " words exceed the stream budget: split the batch (fewer distinct seeds per call)";
+        return MCHB_ERR_ARGUMENT;
+    }
     void *dseeds, *dwords;
     int rc = ensure(h, S_SEEDS, sizeof(uint32_t) * seeds.size(), &dseeds);
     if (rc) return rc;

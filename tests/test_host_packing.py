@@ -97,3 +97,24 @@ def test_call_batch_layout():
         go += G
     assert (cb.hap_total, cb.gl_total, cb.pmax) == (oo, go, int(ploidy.max()))
 
+
+
+def test_many_distinct_seeds_are_split_into_sub_batches(monkeypatch):
+    """every distinct seed costs a pre-generated stream on the device; batches with more
+    distinct per-item seeds than MAX_DISTINCT_SEEDS run as consecutive sub-batches, results joined."""
+    from mchap_b200.assemble import mcmc
+
+    calls = []
+
+    class Fake(object):
+        def fit(self, reads_list, seeds, tag):
+            calls.append((len(reads_list), list(seeds)))
+            return [("r", s) for s in seeds], np.asarray(seeds)
+
+    monkeypatch.setattr(mcmc, "MAX_DISTINCT_SEEDS", 4)
+    seeds = np.arange(10)
+    out = mcmc.split_by_seeds(Fake(), "fit", 10, seeds, dict(reads_list=list(range(10)), seeds=seeds), dict(tag=1))
+    assert [c[0] for c in calls] == [4, 4, 2]
+    assert [o[1] for o in out[0]] == list(range(10)) and out[1].tolist() == list(range(10))
+    assert mcmc.split_by_seeds(Fake(), "fit", 10, np.zeros(10, dtype=int), {}, {}) is None
+    assert mcmc.split_by_seeds(Fake(), "fit", 10, None, {}, {}) is None
