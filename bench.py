@@ -81,6 +81,41 @@ def fragments(depth, n_pos):
 
 
 # ----------------------------------------------------------------------------- CPU arms
+def host_cores():
+    """Cores this process may really use: os.cpu_count() counts the machine's logical CPUs, the
+    scheduler affinity and the cgroup CPU quota say how many of them the container gets (round 1's
+    CPU arm did not speed up from 16 to 32 threads: the 8-GPU box reports 32 logical CPUs)."""
+    info = {"cpu_count": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["cpu_count"]
+    quota = None
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt[0] != "max":
+            quota = float(txt[0]) / float(txt[1])
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    info["cgroup_quota"] = quota
+    used = min(info["cpu_count"], info["affinity"])
+    if quota:
+        used = max(1, min(used, int(round(quota))))
+    info["used"] = used
+    return info
+
+
+def n_cores():
+    return host_cores()["used"]
+
+
+
 def port_pool(work, n_items, cores):
     """C oracle (oracle/mchap_oracle.c: a port of the reference's numba path) over `cores` threads,
     items split like the reference's --cores scheme (np.array_split)."""
@@ -136,7 +171,7 @@ def run_reference(args, rank):
     the C port of the oracle under a thread pool only where numba / oracle/_ref is missing."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = n_cores()
     frag = args.fragments or fragments(DEPTH, N_POS)
     kind = reference_kind()
     # about 3-4 s of work per step on every core (numba: ~2e4 steps/s/core, port: ~6e4)
@@ -173,7 +208,7 @@ def run_reference(args, rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "ploidy": PLOIDY, "n_pos": N_POS, "depth": DEPTH, "fragments": frag,
                    "chains": CHAINS, "mcmc_steps": MCMC_STEPS, "items_per_step": n_items},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "host": host_cores(),
                          "note": "DenovoMCMC.fit of mchap v0.11.1 (numba) per item, as application/assemble.py:123-143 "
                                  "calls it" if kind == "reference" else "C port of the numba path (oracle/mchap_oracle.c)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -328,7 +363,7 @@ def config_call_exact(R, dev, args, peak_tf, cpu):
     if cpu:
         from oracle import oracle as o
 
-        cores = os.cpu_count() or 1
+        cores = n_cores()
         n_cpu = min(n, 40 * cores)
 
         def work(idx):
@@ -393,7 +428,7 @@ def config_call_mcmc(R, dev, args, peak_tf, cpu):
     if cpu:
         from oracle import oracle as o
 
-        cores = os.cpu_count() or 1
+        cores = n_cores()
         n_cpu = min(n, 2 * cores)
 
         def work(idx):
@@ -479,7 +514,7 @@ def config_octoploid(R, dev, args, peak_tf, cpu):
     if cpu:
         from oracle import oracle as o
 
-        cores = os.cpu_count() or 1
+        cores = n_cores()
         n_cpu, s_cpu = cores, 150
         its = [b.item(i) for i in range(n_cpu)]
 
@@ -742,10 +777,10 @@ def run_b200(args, rank, world):
 
     cpu = None
     if cpu_ok:
-        cores = os.cpu_count() or 1
+        cores = n_cores()
         kind = reference_kind()
         if kind == "reference":
-            n_cpu = args.cpu_items or 12 * cores
+            n_cpu = args.cpu_items or 120 * cores
             v, dt, used = cpu_numba_assemble(n_cpu, cores, frag)
             cpu = {"value": v, "unit": UNIT, "cores": used, "kind": "reference",
                    "sample": "%d of the %d locus x sample items of the workload, %.1f s; mchap v0.11.1 DenovoMCMC.fit "
@@ -758,6 +793,7 @@ def run_b200(args, rank, world):
             cpu = port
         else:
             cpu["port"] = port
+        cpu["host"] = host_cores()
 
     if rank == 0:
         line = {

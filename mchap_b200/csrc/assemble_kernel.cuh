@@ -139,9 +139,9 @@ enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC
 #define MCHB_EXACT_SERIAL_MAX 8
 
 // entries of the per-slot memo of screened structural steps (direct mapped): 128 in the one-chunk
-// kernels; 32 in the kernels of the large shapes, where shared memory decides how many warps an
-// SM holds (configs[3]: 58.4 -> 56.1 KB per warp, four warps per SM instead of three)
-#define MCHB_SCACHE_LOG2(CH) ((CH) == 1 ? 7 : 5)
+// kernels, 64 in the two-chunk kernels (the most that keeps 16 warps per SM at the headline shape),
+// 32 in the kernels of the large shapes, where shared memory decides how many warps an SM holds
+#define MCHB_SCACHE_LOG2(CH) ((CH) == 1 ? 7 : ((CH) == 2 ? 6 : 5))
 #define MCHB_SCACHE_N(CH) (1 << MCHB_SCACHE_LOG2(CH))
 struct ScEntry {
     uint32_t epoch;     // state epoch of the slot when the entry was filled

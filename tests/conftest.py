@@ -17,6 +17,22 @@ def pytest_configure(config):
 
 
 def _has_gpu():
+    """A CUDA device as the library sees it: mchb_create on device 0 (no torch needed); torch's
+    answer only where the library cannot be loaded at all."""
+    try:
+        import ctypes
+
+        from mchap_b200 import _lib
+
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = lib.mchb_create(0, ctypes.byref(h))
+        if rc == _lib.MCHB_OK:
+            lib.mchb_destroy(h)
+            return True
+        return False
+    except Exception:
+        pass
     try:
         import torch
 
