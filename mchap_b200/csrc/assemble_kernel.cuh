@@ -87,6 +87,7 @@ struct AsmArgs {
     int32_t o_cnt, o_q, o_dist, o_oll, o_opr, o_lgdisp, o_homlp, o_llk_t, o_key, o_sc, o_perm, o_het, o_fixa,
         o_nall, o_opt0, o_opt1, o_ivb, o_ivp, o_ring, o_q32, o_rat, o_c32, o_rpc, o_bcs, o_epoch, o_mcache, o_scache,
         o_wmap, o_inv, o_hot, o_hmap, o_rank;
+    int32_t scache_n, scache_tri; // entries of the structural memo per slot; > 0: directly indexed, intervals per type
     int32_t sort_recorded;       // record every step with its haplotypes sorted (assemble/classes.py:265-278)
     // tres = state slots resident in shared memory: tmax normally; 1 when the per-temperature
     // tables of a large shape would otherwise leave only one warp per SM — then the slot of the
@@ -138,11 +139,15 @@ enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC
 // loop instead of one exact evaluation per needy sub-step
 #define MCHB_EXACT_SERIAL_MAX 8
 
-// entries of the per-slot memo of screened structural steps (direct mapped): 128 in the one-chunk
-// kernels, 64 in the two-chunk kernels (the most that keeps 16 warps per SM at the headline shape),
-// 32 in the kernels of the large shapes, where shared memory decides how many warps an SM holds
-#define MCHB_SCACHE_LOG2(CH) ((CH) == 1 ? 7 : ((CH) == 2 ? 6 : 5))
-#define MCHB_SCACHE_N(CH) (1 << MCHB_SCACHE_LOG2(CH))
+// Per-slot memo of screened structural steps, keyed by (type, start, stop).  When the table can hold
+// every key of the class's longest item — 2 types x nmax (nmax + 1) / 2 intervals: 72 entries at 8
+// SNVs — it is indexed directly (no collisions: a chain sitting in a mode never screens an interval
+// twice); otherwise it is a direct-mapped hash table of MCHB_SCACHE_HASH_N(CH) entries.  The budgets
+// keep 16 warps per SM at the headline shape (one and two read chunks) and are small where shared
+// memory decides how many warps an SM holds (three and more chunks).
+#define MCHB_SCACHE_HASH_LOG2(CH) ((CH) == 1 ? 7 : ((CH) == 2 ? 6 : 5))
+#define MCHB_SCACHE_HASH_N(CH) (1 << MCHB_SCACHE_HASH_LOG2(CH))
+#define MCHB_SCACHE_DIRECT_MAX(CH) ((CH) == 1 ? 128 : ((CH) == 2 ? 96 : 32))
 struct ScEntry {
     uint32_t epoch;     // state epoch of the slot when the entry was filled
     uint32_t key;       // (type, start, stop)
@@ -384,7 +389,7 @@ __device__ __noinline__ void slot_copy(const AsmArgs &a, unsigned char *sm, int 
     const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned char *back = a.slot_backing + ((size_t)warp_global * a.tmax + slot) * a.slot_bytes;
     const int32_t offs[7] = {a.o_q, a.o_mcache, a.o_key, a.o_scache, a.o_q32, a.o_rpc, a.o_epoch};
-    const int32_t lens[7] = {MCHB_ASM_Q_GLOBAL(CH) ? 0 : a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, MCHB_SCACHE_N(CH) * (int)sizeof(ScEntry),
+    const int32_t lens[7] = {MCHB_ASM_Q_GLOBAL(CH) ? 0 : a.pmax * UPAD * 8, 2 * a.pmax * a.nmax * 8, a.pmax * 8, a.scache_n * (int)sizeof(ScEntry),
                              a.pmax * UPAD * 4, UPAD * 4, 8};
     __syncwarp();
     size_t boff = 0;
@@ -511,7 +516,7 @@ struct AsmCtx {
         return reinterpret_cast<double *>(sm + a.o_mcache) + (size_t)s * 2 * a.pmax * a.nmax;
     }
     __device__ __forceinline__ ScEntry *scache(int s) const {
-        return reinterpret_cast<ScEntry *>(sm + a.o_scache) + (size_t)s * MCHB_SCACHE_N(CH);
+        return reinterpret_cast<ScEntry *>(sm + a.o_scache) + (size_t)s * a.scache_n;
     }
     __device__ __forceinline__ void bump_epoch(int s) {
         uint32_t *e = epoch();
@@ -1158,7 +1163,8 @@ struct AsmCtx {
         // ---- memo of this (type, interval) for the slot's current state
         const uint32_t ep = epoch()[s];
         const uint32_t skey = ((uint32_t)step_type << 16) | ((uint32_t)start << 8) | (uint32_t)stop;
-        ScEntry *ent = scache(s) + ((skey * 2654435761u) >> (32 - MCHB_SCACHE_LOG2(CH)));
+        ScEntry *ent = scache(s) + (a.scache_tri > 0 ? step_type * a.scache_tri + ((stop * (stop - 1)) >> 1) + start
+                                                      : (int)((skey * 2654435761u) >> (32 - MCHB_SCACHE_HASH_LOG2(CH))));
         double u = 0.0;
         bool have_u = false;
         if (ent->epoch == ep && ent->key == skey && ent->temp == (float)temp) {
@@ -1793,7 +1799,7 @@ __global__ void __launch_bounds__(MCHB_ASM_MAXTHREADS(CH), MCHB_ASM_MINCTAS(CH))
         uint32_t *e = c.epoch();
         for (int i = lane; i < 2 * a.tres; i += 32) e[i] = i < a.tres ? 1u : 0u;
         ScEntry *sc0 = c.scache(0);
-        for (int i = lane; i < a.tres * MCHB_SCACHE_N(CH); i += 32) sc0[i].epoch = 0u;
+        for (int i = lane; i < a.tres * a.scache_n; i += 32) sc0[i].epoch = 0u;
         __syncwarp();
         if (CH >= 2 && a.tres < a.tmax) {
             // every slot of the backing store starts from the same empty memo state

@@ -459,7 +459,13 @@ size_t asm_layout(const AsmGeom &g, int ch, int tres, AsmArgs &args) {
     args.o_bcs = take((size_t)(g.maxopt + 1) * 8, 8);
     args.o_epoch = take((size_t)tres * 2 * 4, 8);
     args.o_mcache = take((size_t)tres * 2 * g.pmax * g.nmax * 8, 8);
-    args.o_scache = take((size_t)tres * MCHB_SCACHE_N(ch) * sizeof(ScEntry), 8);
+    {
+        const int tri = g.nmax * (g.nmax + 1) / 2;
+        const int direct_max = MCHB_SCACHE_DIRECT_MAX(ch);
+        args.scache_tri = 2 * tri <= direct_max ? tri : 0;
+        args.scache_n = args.scache_tri > 0 ? 2 * tri : MCHB_SCACHE_HASH_N(ch);
+    }
+    args.o_scache = take((size_t)tres * args.scache_n * sizeof(ScEntry), 8);
     args.o_wmap = take((size_t)g.pmax * g.nmax * 2, 2);
     args.o_inv = take(32 * 4, 4);
     args.o_hot = take((size_t)g.tmax * 4 * 4, 4);
@@ -530,7 +536,7 @@ int launch_assemble(mchb_handle *h, cudaStream_t stream, AsmArgs &args, const As
         const size_t upad = (size_t)CH * 32;
         auto r8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
         const size_t slot_bytes = (r8(MCHB_ASM_Q_GLOBAL(CH) ? 0 : g.pmax * upad * 8) + r8((size_t)2 * g.pmax * g.nmax * 8) + r8((size_t)g.pmax * 8) +
-                                   r8(MCHB_SCACHE_N(CH) * sizeof(ScEntry)) + r8(g.pmax * upad * 4) + r8(upad * 4) + r8(8) + 15) &
+                                   r8((size_t)args.scache_n * sizeof(ScEntry)) + r8(g.pmax * upad * 4) + r8(upad * 4) + r8(8) + 15) &
                                   ~(size_t)15;
         void *back;
         int rc = ensure(h, backing_slot, slot_bytes * (size_t)g.tmax * (size_t)grid * warps_per_cta, &back);
