@@ -50,9 +50,9 @@ WORKLOAD = ("synthetic tetraploid assemble: 10k loci x 8 SNVs x 100 samples, dep
             "2 chains x 1500 steps")
 
 # DRAM bytes per (locus, sample) item of assemble_kernel<1,false>, from the committed ncu capture
-# (profiles/r02_c1_ncu_raw.csv): dram__bytes_read.sum + dram__bytes_write.sum = 817.2 MB for the 6801 items
+# (profiles/r02_d1_ncu_raw.csv): dram__bytes_read.sum + dram__bytes_write.sum = 820.3 MB for the 6801 items
 # of that launch (the items with <= 32 distinct reads of a 14208-item batch at depth 40)
-NCU_DRAM_BYTES_PER_ITEM = 120164.0
+NCU_DRAM_BYTES_PER_ITEM = 120620.0
 
 
 def parse_args():
@@ -754,7 +754,7 @@ def run_b200(args, rank, world):
         pass
     roofline = fp64_roofline(flops, dev_time, peak_tf, "assemble_kernel<1> + assemble_kernel<2> (items with <= 32 / 33-64 distinct reads)", {
         "traffic": NCU_DRAM_BYTES_PER_ITEM * items_per_step, "traffic_per_item": NCU_DRAM_BYTES_PER_ITEM,
-        "traffic_source": "profiles/r02_c1_ncu_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) of one "
+        "traffic_source": "profiles/r02_d1_ncu_raw.csv: (dram__bytes_read.sum + dram__bytes_write.sum) of one "
                           "`ncu --set full` launch of assemble_kernel<1,false> / its 6801 items, scaled to the %d items "
                           "of one bench step; algorithmic bytes per item = %.0f" % (
                               items_per_step, (in_bytes + out_bytes) / items_per_step),
