@@ -72,11 +72,17 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
     // Memo: the categorical distribution of slot k is a function of (k, genotype) only, and a
     // chain that sits in a mode asks for the same one step after step.  Per slot: the genotype it
     // was computed for, its cumulative sums (what random_choice searches) and the candidates' llks.
+    // Two entries (ways) per slot, least recently used replaced: a chain that leaves its mode for a
+    // step or two finds the mode's distributions again when it returns (measured: 233 M -> 298 M MCMC
+    // steps/s at configs[4]; three and four ways lose more to shared memory than they gain).  The Gibbs
+    // conditional of slot k does not depend on the allele slot k holds, so that allele is not part of
+    // its key (the Metropolis-Hastings distribution is relative to the current allele: there it is).
     const bool memo = a.memo_off >= 0;
-    double *mcs = reinterpret_cast<double *>(sm + (memo ? a.memo_off : 0));   // [pmax][hmax] cumulative sums
-    double *mls = mcs + (size_t)a.pmax * a.hmax;                              // [pmax][hmax] llks
-    int *mkey = reinterpret_cast<int *>(mls + (size_t)a.pmax * a.hmax);       // [pmax][pmax] genotype of the entry
-    int *mvalid = mkey + a.pmax * a.pmax;                                     // [pmax]
+    double *mcs = reinterpret_cast<double *>(sm + (memo ? a.memo_off : 0));   // [pmax][2][hmax] cumulative sums
+    double *mls = mcs + (size_t)2 * a.pmax * a.hmax;                          // [pmax][2][hmax] llks
+    int *mkey = reinterpret_cast<int *>(mls + (size_t)2 * a.pmax * a.hmax);   // [pmax][2][pmax] genotype of the entry
+    int *mvalid = mkey + 2 * a.pmax * a.pmax;                                 // [pmax][2]
+    int *mlru = mvalid + 2 * a.pmax;                                          // [pmax] way to replace next
 
     for (;;) {
         int w = 0;
@@ -97,7 +103,8 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
         long long evals = 0;
         int err = 0;
         if (memo) {
-            for (int k = lane; k < a.pmax; k += 32) mvalid[k] = 0;
+            for (int k = lane; k < 2 * a.pmax; k += 32) mvalid[k] = 0;
+            for (int k = lane; k < a.pmax; k += 32) mlru[k] = 0;
         }
 
         // ---- raw table t[r][h] (likelihood.py:48-58 per haplotype), counts
@@ -230,24 +237,32 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                 for (int jj = 0; jj < P && !err; jj++) {
                     const int k = ord[jj];
                     if (memo) {
-                        bool same = mvalid[k] != 0;
-                        for (int s = lane; s < P; s += 32) same = same && (mkey[k * P + s] == gs[s]);
-                        if (__all_sync(MCHB_FULL, same)) {
+                        bool same0 = mvalid[2 * k] != 0, same1 = mvalid[2 * k + 1] != 0;
+                        for (int s = lane; s < P; s += 32) {
+                            const bool own = a.step_type == 0 && s == k;
+                            same0 = same0 && (own || mkey[(2 * k) * P + s] == gs[s]);
+                            same1 = same1 && (own || mkey[(2 * k + 1) * P + s] == gs[s]);
+                        }
+                        const bool hit0 = __all_sync(MCHB_FULL, same0), hit1 = __all_sync(MCHB_FULL, same1);
+                        if (hit0 || hit1) {
                             // same draw from the remembered cumulative sums (jitutils.py:77-92)
+                            const int way = hit0 ? 0 : 1;
+                            const double *wcs = mcs + (size_t)(2 * k + way) * H, *wls = mls + (size_t)(2 * k + way) * H;
                             evals += H;
                             const double u = ws.next_double();
                             int choice = 0;
                             for (int a0 = 0; a0 < H; a0 += 32) {
                                 const int al = a0 + lane;
-                                choice += __popc(__ballot_sync(MCHB_FULL, al < H && mcs[k * H + al] <= u));
+                                choice += __popc(__ballot_sync(MCHB_FULL, al < H && wcs[al] <= u));
                             }
                             if (choice >= H) {
                                 err = MCHB_ITEM_CHOICE_RANGE;
                                 break;
                             }
-                            llk_last = mls[k * H + choice];
+                            llk_last = wls[choice];
                             __syncwarp();
                             gs[k] = choice;
+                            if (lane == 0) mlru[k] = 1 - way;
                             __syncwarp();
                             continue;
                         }
@@ -372,8 +387,9 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                         }
                         v += carry;
                         if (memo && al < H) {
-                            mcs[k * H + al] = v;
-                            mls[k * H + al] = ls[al];
+                            const int way = mlru[k];
+                            mcs[(size_t)(2 * k + way) * H + al] = v;
+                            mls[(size_t)(2 * k + way) * H + al] = ls[al];
                         }
                         choice += __popc(__ballot_sync(MCHB_FULL, al < H && v <= u));
                         carry = __shfl_sync(MCHB_FULL, v, 31);
@@ -385,8 +401,13 @@ __global__ void __launch_bounds__(128) call_mcmc_kernel(const __grid_constant__ 
                     llk_last = ls[choice];
                     __syncwarp();
                     if (memo) {
-                        for (int s = lane; s < P; s += 32) mkey[k * P + s] = gs[s];
-                        if (lane == 0) mvalid[k] = 1;
+                        const int way = mlru[k];
+                        for (int s = lane; s < P; s += 32) mkey[(2 * k + way) * P + s] = gs[s];
+                        __syncwarp();
+                        if (lane == 0) {
+                            mvalid[2 * k + way] = 1;
+                            mlru[k] = 1 - way;
+                        }
                     }
                     __syncwarp();
                     gs[k] = choice;

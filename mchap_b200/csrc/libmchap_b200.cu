@@ -1422,7 +1422,7 @@ extern "C" int mchb_call_mcmc_batch(mchb_handle *h, int mem, const mchb_call_mcm
         ~(size_t)15;
     // memo of the conditional distributions (cumulative sums + llks per genotype slot): kept in
     // shared memory when it is small next to the read x haplotype table
-    const size_t memo_bytes = ((size_t)g.pmax * g.hmax * 16 + (size_t)g.pmax * g.pmax * 4 + (size_t)g.pmax * 4 + 15) & ~(size_t)15;
+    const size_t memo_bytes = (2 * ((size_t)g.pmax * g.hmax * 16 + (size_t)g.pmax * g.pmax * 4 + (size_t)g.pmax * 4) + (size_t)g.pmax * 4 + 15) & ~(size_t)15;  // two ways per slot
     const bool use_memo = memo_bytes <= 16384;
     const size_t memo_off = per_warp;
     if (use_memo) per_warp += memo_bytes;
