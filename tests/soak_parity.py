@@ -71,6 +71,43 @@ def run_shape(name, n_items, steps, ploidy, n_pos, depth, temps=(1.0,), inbreedi
                       "oracle_s": round(t_cpu, 2)}), flush=True)
 
 
+def run_call_shape(name, n_items, steps, ploidy, n_haps, n_pos, depth, step_type, prior=None, seed=0):
+    """The same for CallingMCMC.fit_batch (mchap call) against the oracle's calling_fit."""
+    from mchap_b200.calling import CallingMCMC
+    from mchap_b200.synth import synth_haplotype_panel
+
+    batch, panels, _ = synth_haplotype_panel(n_items, n_haps, n_pos, ploidy, depth=depth, seed=seed)
+    reads = [batch.item(i)[0] for i in range(n_items)]
+    counts = [batch.item(i)[1] for i in range(n_items)]
+    model = CallingMCMC(ploidy=ploidy, haplotypes=None, steps=steps, chains=2, random_seed=seed + 1, step_type=step_type,
+                        prior=prior)
+    t0 = time.perf_counter()
+    traces, results = model.fit_batch(reads, counts, haplotypes_list=list(panels), return_results=True)
+    t_gpu = time.perf_counter() - t0
+
+    def ref(i):
+        return O.calling_fit(reads[i], counts[i], ploidy, panels[i], prior=prior, steps=steps, chains=2,
+                             random_seed=seed + 1, step_type=step_type)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        refs = list(ex.map(ref, range(n_items)))
+    t_cpu = time.perf_counter() - t0
+    worst = 0.0
+    for i, r in enumerate(refs):
+        if not np.array_equal(traces[i].genotypes, r["genotypes"]) or int(results["rng_words"][i]) != int(r["words"]):
+            print(json.dumps({"shape": name, "item": i, "mismatch": "genotypes or words"}))
+            sys.exit(1)
+        rel = np.max(np.abs(traces[i].llks - r["llks"]) / np.maximum(np.abs(r["llks"]), 1e-300))
+        worst = max(worst, float(rel))
+        if rel > 1e-9:
+            print(json.dumps({"shape": name, "item": i, "mismatch": "llks", "rel": float(rel)}))
+            sys.exit(1)
+    print(json.dumps({"shape": name, "items": n_items, "mcmc_steps_compared": n_items * 2 * steps,
+                      "identical_traces": True, "worst_llk_rel_err": worst, "gpu_s": round(t_gpu, 2),
+                      "oracle_s": round(t_cpu, 2)}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--items", type=int, default=1500)
@@ -93,3 +130,9 @@ if __name__ == "__main__":
               133, temps=(0.01, 0.1, 0.5, 1.0), seed=109)
     run_shape("hexaploid 8 SNV, 80 fragments, temperatures 0.05/0.3/1, inbreeding 0.1", n // 6, s // 2, 6, 8, 80,
               temps=(0.05, 0.3, 1.0), inbreeding=0.1, seed=110)
+    # mchap call (two-entry memo of the conditional distributions)
+    run_call_shape("call: tetraploid, 32 haplotypes, Gibbs (configs[4])", n // 2, s, 4, 32, 8, 53, "Gibbs", seed=201)
+    run_call_shape("call: tetraploid, 32 haplotypes, Gibbs, prior (0.1, flat)", n // 2, s, 4, 32, 8, 53, "Gibbs",
+                   prior=(0.1, None), seed=202)
+    run_call_shape("call: hexaploid, 12 haplotypes, Metropolis-Hastings", n // 2, s, 6, 12, 8, 53, "Metropolis-Hastings",
+                   prior=(0.2, None), seed=203)
