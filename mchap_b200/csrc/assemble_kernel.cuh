@@ -130,7 +130,14 @@ enum { SC_LUH = 0, SC_LG_SUMDISP, SC_LG_P_SUMDISP, SC_LG_DISP, SC_INBREEDING, SC
 // (SC_ERR_MUT / SC_ERR_STR, per item) bounds |screened llk - exact llk| — derivation in DESIGN.md
 // section 4 'Error bound of the float32 screening' — and the slack covers the float32 log of the
 // uniform (<= 3.2e-5), the float conversion of t and the double roundings of the exact path.
+#ifndef MCHB_SCREEN_SLACK
 #define MCHB_SCREEN_SLACK 1.0e-3
+#endif
+// Test aid (profiles/bound_sensitivity.sh): scales both error bounds; a build with a bound that is
+// too small must be caught by the parity harness (it is: see profiles/r02_bound_sensitivity.txt).
+#ifndef MCHB_SCREEN_ERR_SCALE
+#define MCHB_SCREEN_ERR_SCALE 1.0
+#endif
 // reads whose screened probability falls below this fraction of the current one make the sub-step
 // needy (the error bound is proportional to 1 / this)
 #define MCHB_SCREEN_MIN_RATIO 1.0e-4f
@@ -1755,8 +1762,8 @@ __device__ __noinline__ int assemble_item_setup(const AsmArgs &a, unsigned char 
             const double umax_reads = (double)U;
             //  both: float32 underflow of a term (<= 2^-126 against rp > 1e-30): 1.2e-8 per operation.
             const double under = 1.2e-8 * (double)(N + P + 2);
-            scv[SC_ERR_MUT] = csum * (1.02 * ((double)(P + 2) * 9.0e-4) + 3.2e-5 + 4.3e-6 * umax_reads + under);
-            scv[SC_ERR_STR] = csum * (1.02 * 6.0e-8 * (double)(3 * N + P + 1) + 3.2e-5 + 4.3e-6 * (double)(CH + 1) + under);
+            scv[SC_ERR_MUT] = MCHB_SCREEN_ERR_SCALE * csum * (1.02 * ((double)(P + 2) * 9.0e-4) + 3.2e-5 + 4.3e-6 * umax_reads + under);
+            scv[SC_ERR_STR] = MCHB_SCREEN_ERR_SCALE * csum * (1.02 * 6.0e-8 * (double)(3 * N + P + 1) + 3.2e-5 + 4.3e-6 * (double)(CH + 1) + under);
         }
         __syncwarp();
     }
