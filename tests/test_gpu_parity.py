@@ -754,3 +754,45 @@ def test_assemble_hundreds_of_distinct_reads_vs_oracle(dev, oracle, depth, ploid
     if depth == 1024:
         res = model.fit_batch(big, [None] * 4, errors="return", raw=True)
         assert isinstance(res[3], NotImplementedError) and not isinstance(res[0], BaseException)
+
+
+@pytest.mark.parametrize("temps,inbreeding,depth", [
+    ((0.01, 1.0), None, 30),
+    ((0.02, 0.3, 1.0), 0.1, 30),
+    ((0.01, 1.0), None, 90),      # three read chunks: tables in global memory
+])
+def test_assemble_heated_replicas_with_mixed_allele_counts(dev, oracle, temps, inbreeding, depth):
+    """Hot mode (a replica that accepts most proposals decides its sub-steps one by one, screened for
+    certain acceptance and rejection, the exact log-likelihood evaluated lazily) on items that mix
+    bi-allelic positions with three- and four-allelic ones (those take the serial exact step in the
+    middle of the hot loop), plus the interval-arithmetic draws of the structural steps."""
+    from mchap_b200 import DenovoMCMC
+
+    rng = np.random.default_rng(int(depth + 100 * temps[0] * 100))
+    reads, counts, nalls = [], [], []
+    for i in range(10):
+        N = int(rng.integers(3, 8))
+        A = 4
+        na = rng.integers(2, A + 1, size=N).astype(np.int8)
+        na[rng.integers(0, N)] = 2                      # at least one bi-allelic position
+        haps = np.stack([rng.integers(0, na[j], size=4) for j in range(N)], axis=1)
+        src = rng.integers(0, 4, size=depth)
+        calls = haps[src]
+        r = np.full((depth, N, A), 0.0008)
+        np.put_along_axis(r, calls[:, :, None], 0.9976, axis=2)
+        r *= 1 + rng.random(r.shape) * 1e-3                # all reads distinct
+        for j in range(N):
+            r[:, j, na[j]:] = 0
+        r[rng.random((depth, N)) < 0.2] = np.nan
+        reads.append(r)
+        counts.append(np.ones(depth, dtype=np.int64))
+        nalls.append(na)
+    model = DenovoMCMC(ploidy=4, n_alleles=None, inbreeding=inbreeding, steps=80, chains=2, temperatures=temps,
+                       random_seed=7)
+    out, results = model.fit_batch(reads, counts, n_alleles_list=nalls, return_results=True, raw=True)
+    for i in range(10):
+        ref = _oracle_fit(oracle, model, reads[i], counts[i], nalls[i])
+        np.testing.assert_array_equal(out[i][0], ref["genotypes"], err_msg="item %d" % i)
+        close(out[i][1], ref["llks"])
+        assert results["rng_words"][i] == ref["words"]
+        assert results["llk_evals"][i] == ref["llk_evals"]
