@@ -440,9 +440,13 @@ class CallBatch:
         Us, Ns, As, Hs = [0] * n, [0] * n, [0] * n, [0] * n   # per-item scalars, assigned column-wise below
         inbs, foffs = [np.nan] * n, [-1] * n
         fo = 0
+        f64, i8, nd = np.float64, np.int8, np.ndarray
         for i in range(n):
-            r = np.ascontiguousarray(reads_list[i], dtype=np.float64)
-            hp = np.ascontiguousarray(haplotypes_list[i], dtype=np.int8)
+            r, hp = reads_list[i], haplotypes_list[i]
+            if not (type(r) is nd and r.dtype == f64 and r.flags.c_contiguous):
+                r = np.ascontiguousarray(r, dtype=f64)
+            if not (type(hp) is nd and hp.dtype == i8 and hp.flags.c_contiguous):
+                hp = np.ascontiguousarray(hp, dtype=i8)
             assert r.ndim == 3 and hp.ndim == 2 and hp.shape[1] == r.shape[1]
             Us[i], Ns[i], As[i] = r.shape
             H = Hs[i] = hp.shape[0]
@@ -456,16 +460,17 @@ class CallBatch:
                     foffs[i] = fo
                     fs.append(fr)
                     fo += H
-            rs.append(r.reshape(-1))
-            hs.append(hp.reshape(-1))
+            rs.append(r)      # (joined with axis=None below: no per-item flattening)
+            hs.append(hp)
             if use_counts:
                 c = counts_list[i]
                 cs.append(np.ones(Us[i], dtype=np.int64) if c is None else np.ascontiguousarray(c, dtype=np.int64))
         U_, N_, A_, H_ = (np.asarray(x, dtype=np.int64) for x in (Us, Ns, As, Hs))
         excl = lambda x: np.concatenate([[0], np.cumsum(x)[:-1]]) if n else np.zeros(0, dtype=np.int64)
         memo = {}
-        self.n_genotypes = np.array(
-            [memo.setdefault(k, count_genotypes(*k)) for k in zip(Hs, ploidies.tolist())], dtype=np.int64)
+        for k in set(zip(Hs, ploidies.tolist())):
+            memo[k] = count_genotypes(*k)
+        self.n_genotypes = np.array([memo[k] for k in zip(Hs, ploidies.tolist())], dtype=np.int64)
         items = np.zeros(n, dtype=CALL_ITEM_DTYPE)
         items["reads_off"] = excl(U_ * N_ * A_)
         items["counts_off"] = excl(U_) if use_counts else 0
@@ -480,9 +485,9 @@ class CallBatch:
             self.haps = device.pinned_concatenate(hs, np.int8)
             self.counts = device.pinned_concatenate(cs, np.int64) if use_counts else None
         else:
-            self.reads = np.concatenate(rs) if rs else np.zeros(0)
-            self.haps = np.concatenate(hs) if hs else np.zeros(0, dtype=np.int8)
-            self.counts = np.concatenate(cs) if use_counts else None
+            self.reads = np.concatenate(rs, axis=None) if rs else np.zeros(0)
+            self.haps = np.concatenate(hs, axis=None) if hs else np.zeros(0, dtype=np.int8)
+            self.counts = np.concatenate(cs, axis=None) if use_counts else None
         self.freqs = np.concatenate(fs) if fs else None
         self.hap_total = int(H_.sum())
         self.gl_total = int(self.n_genotypes.sum())
