@@ -118,3 +118,25 @@ def test_many_distinct_seeds_are_split_into_sub_batches(monkeypatch):
     assert [o[1] for o in out[0]] == list(range(10)) and out[1].tolist() == list(range(10))
     assert mcmc.split_by_seeds(Fake(), "fit", 10, np.zeros(10, dtype=int), {}, {}) is None
     assert mcmc.split_by_seeds(Fake(), "fit", 10, None, {}, {}) is None
+
+
+def test_fragments_for_depth_matches_the_window_model():
+    """53 fragments give depth 40 at every SNV of an 8-SNV locus, 133 give depth 100 at 16 SNVs
+    (windows cover 50-100 % of the locus)."""
+    from mchap_b200.synth import fragments_for_depth, synth_items
+
+    assert fragments_for_depth(40, 8) == 53 and fragments_for_depth(100, 16) == 133
+    b = synth_items(400, ploidy=4, n_pos=8, depth=53, seed=3)
+    depth_at_snv = (b.calls >= 0).mean() * 53
+    assert 38.5 < depth_at_snv < 41.5
+
+
+def test_page_locked_size_classes():
+    """Pooled page-locked blocks: a size class is at most 12.5 % above the request and classes are
+    coarse enough for blocks to be reused by the next batch of about the same size."""
+    from mchap_b200.api import Device
+
+    for n in (1, 70000, 10 ** 6, 123456789, 2_400_000_000):
+        c = Device._pin_class(n)
+        assert c >= n and c >= (1 << 16) and (c <= n * 1.125 + 4096 or n < (1 << 16))
+    assert Device._pin_class(2_400_000_000) == Device._pin_class(2_390_000_000)
